@@ -1,0 +1,139 @@
+"""ctypes binding of libdpm_b200.so (include/dpm_b200.h).
+
+There is no fallback: if the library is missing or the tensors are not on a CUDA device the
+calls raise.  Build it with `python -m deeppointmap_b200.build` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdpm_b200.so")
+
+MAX_STAGES, MAX_BLOCKS = 8, 4
+REG_R, REG_T, REG_RMSE, REG_NCORR, REG_NINLIER, REG_ITERS, REG_STRIDE = 0, 9, 12, 13, 14, 15, 16
+ACT_NONE, ACT_RELU = 0, 1
+
+_ERR = {-1: "shape", -2: "unsupported", -3: "workspace", -4: "cuda", -5: "argument"}
+
+
+class EncoderDesc(ctypes.Structure):
+    _fields_ = [("n_stages", ctypes.c_int), ("in_channel", ctypes.c_int), ("width", ctypes.c_int),
+                ("expansion", ctypes.c_int), ("out_channel", ctypes.c_int), ("upsample_layers", ctypes.c_int),
+                ("npoint", ctypes.c_int * MAX_STAGES), ("n_blocks", ctypes.c_int * MAX_STAGES),
+                ("radius", (ctypes.c_double * MAX_BLOCKS) * MAX_STAGES),
+                ("nsample", (ctypes.c_int * MAX_BLOCKS) * MAX_STAGES)]
+
+
+class DecoderDesc(ctypes.Structure):
+    _fields_ = [("in_channel", ctypes.c_int), ("model_channel", ctypes.c_int), ("attention_layers", ctypes.c_int),
+                ("heads", ctypes.c_int), ("tau", ctypes.c_float), ("eps_offset", ctypes.c_float)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+_vp, _i, _f, _sz, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
+
+_SIGS = {
+    "dpm_version": ([], _i),
+    "dpm_last_error": ([], ctypes.c_char_p),
+    "dpm_launch_count": ([], _ll),
+    "dpm_launch_count_reset": ([], None),
+    "dpm_fps_f32": ([_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp], _i),
+    "dpm_fps_workspace_bytes": ([_i, _i, _i, _i], _sz),
+    "dpm_knn_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp], _i),
+    "dpm_knn_radius_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _sz, _vp], _i),
+    "dpm_ball_query_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp], _i),
+    "dpm_knn_workspace_bytes": ([_i, _i, _i, _i], _sz),
+    "dpm_linear_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "dpm_layernorm_f32": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
+    "dpm_group_ln_relu_max_f32": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "dpm_fp_interp_f32": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "dpm_encoder_forward": ([ctypes.POINTER(EncoderDesc), _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp,
+                             _vp, _vp, _sz, _vp], _i),
+    "dpm_encoder_workspace_bytes": ([ctypes.POINTER(EncoderDesc), _i, _i], _sz),
+    "dpm_encoder_num_weights": ([ctypes.POINTER(EncoderDesc)], _i),
+    "dpm_encoder_out_points": ([ctypes.POINTER(EncoderDesc)], _i),
+    "dpm_registration_forward": ([ctypes.POINTER(DecoderDesc), _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz,
+                                  _vp], _i),
+    "dpm_registration_workspace_bytes": ([ctypes.POINTER(DecoderDesc), _i, _i, _i, _i], _sz),
+    "dpm_loop_detection_forward": ([ctypes.POINTER(DecoderDesc), _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp], _i),
+    "dpm_loop_detection_workspace_bytes": ([ctypes.POINTER(DecoderDesc), _i, _i, _i], _sz),
+    "dpm_decoder_num_weights": ([ctypes.POINTER(DecoderDesc)], _i),
+    "dpm_posenc_f32": ([_vp, _i, _vp, _i, _vp, _i, _i, _vp], _i),
+    "dpm_attention_f32": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp], _i),
+    "dpm_kabsch_f32": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: the CUDA library has not been built "
+                        "(run `python -m deeppointmap_b200.build`). There is no CPU fallback.")
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (args, res) in _SIGS.items():
+                    fn = getattr(L, name)
+                    fn.argtypes = args
+                    fn.restype = res
+                _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().dpm_last_error().decode("utf-8", "replace")
+        kind = _ERR.get(rc, str(rc))
+        exc = ValueError if rc in (-1, -5) else (NotImplementedError if rc == -2 else RuntimeError)
+        raise exc(f"libdpm_b200 {what}: {kind} error: {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("deeppointmap_b200 ops run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class _Workspaces(threading.local):
+    """One growable scratch buffer per (host thread, device, slot)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, device, nbytes: int, slot: str = "default") -> torch.Tensor:
+        key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+        b = self.buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+            self.buf[key] = b
+        return b
+
+
+workspaces = _Workspaces()
+
+
+def launch_count() -> int:
+    return int(lib().dpm_launch_count())
+
+
+def launch_count_reset() -> None:
+    lib().dpm_launch_count_reset()

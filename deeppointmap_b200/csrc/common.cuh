@@ -1,0 +1,109 @@
+// common.cuh -- shared helpers for libdpm_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dpm_b200.h"
+
+namespace dpm {
+
+// ---- error plumbing (thread-local, see dpm_last_error) --------------------------------
+char *err_buf();
+int fail(int code, const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define DPM_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return dpm::fail(DPM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define DPM_CHECK_LAUNCH()                                                                     \
+    do {                                                                                       \
+        dpm::count_launch();                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return dpm::fail(DPM_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                 \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+    } while (0)
+
+#define DPM_TRY(expr)                \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != DPM_OK) return _rc; \
+    } while (0)
+
+// ---- bump allocator over the caller's workspace ---------------------------------------
+struct Arena {
+    char *base;
+    size_t cap, off;
+    bool dry;  // dry run: only measure
+    Arena(void *p, size_t n) : base((char *)p), cap(n), off(0), dry(p == nullptr) {}
+    template <typename T>
+    T *get(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        size_t o = off;
+        off += bytes;
+        if (dry) return nullptr;
+        if (off > cap) return nullptr;
+        return (T *)(base + o);
+    }
+    bool ok() const { return dry || off <= cap; }
+};
+
+int device_sm_count();
+
+// ---- device helpers ---------------------------------------------------------------------
+#ifdef __CUDACC__
+// Exact reference arithmetic: (dx*dx + dy*dy) + dz*dz, fp32, round-to-nearest, no FMA
+// contraction (network/encoder/utils.py:255-256).
+__device__ __forceinline__ float d2_exact(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+// ---- internal launchers shared between translation units ------------------------------
+// xyz4 buffers are float4 (x,y,z,0) rows.
+int fps_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64,
+               int32_t *idx32, float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);
+int knn_launch(const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
+               const int *plen32, int K, float r2, int mode, int64_t *idx64, int32_t *idx32,
+               float *d2out, cudaStream_t st);
+enum { KNN_MODE_KNN = 0, KNN_MODE_HYBRID = 1 };
+int pack_xyz4_launch(const float *src, int B, int N, int D, float4 *dst, cudaStream_t st);
+int lengths_to_i32_launch(const int64_t *len64, int B, int N, int *len32, cudaStream_t st);
+int linear_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res, int ldres,
+                  float *Y, int ldy, int M, int N, int K, int act, cudaStream_t st);
+int linear_batched_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW,
+                          const float *bias, const float *res, int ldres, float *Y, int ldy, long long sY, int M,
+                          int N, int K, int nbatch, int act, cudaStream_t st);
+int layernorm_launch(const float *X, int ldx, const float *gamma, const float *beta, const float *post, int ldpost,
+                     float *Y, int ldy, int M, int C, int act, cudaStream_t st);
+int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *Wxyz,
+                 int ldw, const float *gamma, const float *beta, float radius, float *out, int B, int N, int S,
+                 int K, int Cout, cudaStream_t st);
+int fp_interp_launch(const float4 *xyz1, const float4 *xyz2, const float *fea1, const float *fea2,
+                     const uint8_t *pad2, float *out, int B, int N, int S, int C1, int C2, cudaStream_t st);
+
+}  // namespace dpm

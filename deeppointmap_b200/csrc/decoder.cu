@@ -1,0 +1,953 @@
+// decoder.cu -- Decoder.registration_forward / loop_detection_forward
+// (network/decoder/decoder.py:91-265, descriptor_attention.py, heads.py) as native calls.
+//
+// Token layout: one row per descriptor.  For pair p the M src rows are followed by the N dst
+// rows (R = P*(M+N) rows in total), so every shared-weight layer (projection, in/out
+// projections, MLP, LayerNorms, heads) is ONE launch over all rows of all pairs, and
+// self/cross attention are one launch over 2P (query-range, key-range) problems.
+// Data-dependent shapes of the reference (offset filter, sigma clipping) are restated with
+// counts + masks on the device: there is no host sync anywhere in here.
+#include "common.cuh"
+
+namespace dpm {
+
+// ---------------------------------------------------------------------------------------
+// channel-first descriptors -> row-major features + float4 xyz
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dec_unpack_kernel(const float *__restrict__ src, const float *__restrict__ dst, int M, int N, int Cf,
+                  float *__restrict__ fea, float4 *__restrict__ xyz) {
+    __shared__ float tile[32][33];
+    const int z = blockIdx.z, p = z >> 1, side = z & 1;
+    const int L = side ? N : M;
+    const float *in = (side ? dst : src) + (size_t)p * (Cf + 3) * L;
+    const size_t row0 = (size_t)p * (M + N) + (side ? M : 0);
+    const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    if (l0 >= L) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, l = l0 + tx;
+        tile[r][tx] = (c < Cf && l < L) ? in[(size_t)c * L + l] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int l = l0 + r, c = c0 + tx;
+        if (l < L && c < Cf) fea[(row0 + l) * Cf + c] = tile[tx][r];
+    }
+    if (blockIdx.y == 0 && ty == 0) {
+        const int l = l0 + tx;
+        if (l < L)
+            xyz[row0 + l] = make_float4(in[(size_t)Cf * L + l], in[(size_t)(Cf + 1) * L + l], in[(size_t)(Cf + 2) * L + l], 0.f);
+    }
+}
+
+// PositionEmbeddingCoordsSine.forward (descriptor_attention.py:66-83)
+__global__ void __launch_bounds__(256)
+posenc_kernel(const float *__restrict__ xyz, int ldx, const float *__restrict__ dim_t, int npf, float *__restrict__ emb,
+              int R, int C) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)R * C) return;
+    const int r = (int)(t / C), c = (int)(t % C);
+    float v = 0.f;
+    if (c < 3 * npf) {
+        const int a = c / npf, i = c % npf;
+        const float x = __fmul_rn(xyz[(size_t)r * ldx + a], 3.14159274101257324f);  // coor * fp32(pi)
+        const float pd = __fdiv_rn(x, dim_t[i]);
+        v = (i & 1) ? cosf(pd) : sinf(pd);
+    }
+    emb[t] = v;
+}
+
+int posenc_launch(const float *xyz, int ldx, const float *dim_t, int npf, float *emb, int R, int C, cudaStream_t st) {
+    if (R <= 0 || C <= 0 || npf <= 0) return fail(DPM_ERR_SHAPE, "posenc: bad shape");
+    const long long total = (long long)R * C;
+    posenc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xyz, ldx, dim_t, npf, emb, R, C);
+    DPM_CHECK_LAUNCH();
+    return DPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-head attention core, head_dim 32, fp32, flash-style online softmax.
+// block = 32 queries (lane = query) x 4 warps splitting the keys of each 256-key chunk.
+// ---------------------------------------------------------------------------------------
+constexpr int ATT_KC = 256;
+
+__global__ void __launch_bounds__(128)
+attention_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__ Kp, int ldk,
+                 const float *__restrict__ Vp, int ldv, float *__restrict__ O, int ldo, const int *__restrict__ prob,
+                 int M, int N, int mode) {
+    extern __shared__ __align__(16) float att_smem[];
+    float *Ks = att_smem;                 // [ATT_KC][32]
+    float *Vs = att_smem + ATT_KC * 32;   // [ATT_KC][32]
+    __shared__ float mb[4][32][35];
+
+    const int z = blockIdx.z, head = blockIdx.y;
+    int q0, Lq, k0, Lk;
+    if (prob) {
+        q0 = prob[4 * z]; Lq = prob[4 * z + 1]; k0 = prob[4 * z + 2]; Lk = prob[4 * z + 3];
+    } else {
+        const int p = z >> 1, side = z & 1, base = p * (M + N);
+        q0 = base + (side ? M : 0);
+        Lq = side ? N : M;
+        const int kvside = mode ? !side : side;  // mode 0: self, 1: cross
+        k0 = base + (kvside ? M : 0);
+        Lk = kvside ? N : M;
+    }
+    if (blockIdx.x * 32 >= Lq) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qi = blockIdx.x * 32 + lane;
+    const bool qvalid = qi < Lq;
+
+    float qv[32], acc[32];
+    {
+        const float *qp = Q + (size_t)(q0 + (qvalid ? qi : 0)) * ldq + head * 32;
+        const float scale = 0.17677669529663687f;  // sqrt(1/32)
+#pragma unroll
+        for (int d4 = 0; d4 < 8; ++d4) {
+            const float4 t = *reinterpret_cast<const float4 *>(qp + 4 * d4);
+            qv[4 * d4] = t.x * scale; qv[4 * d4 + 1] = t.y * scale; qv[4 * d4 + 2] = t.z * scale; qv[4 * d4 + 3] = t.w * scale;
+        }
+#pragma unroll
+        for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+    }
+    float m = -__int_as_float(0x7f800000), l = 0.f;
+
+    for (int c0 = 0; c0 < Lk; c0 += ATT_KC) {
+        const int cn = min(ATT_KC, Lk - c0);
+        __syncthreads();
+        for (int e = tid; e < cn * 8; e += 128) {
+            const int key = e >> 3, part = e & 7;
+            const size_t row = (size_t)(k0 + c0 + key);
+            reinterpret_cast<float4 *>(Ks)[e] = *reinterpret_cast<const float4 *>(Kp + row * ldk + head * 32 + 4 * part);
+            reinterpret_cast<float4 *>(Vs)[e] = *reinterpret_cast<const float4 *>(Vp + row * ldv + head * 32 + 4 * part);
+        }
+        __syncthreads();
+        const int per = (cn + 3) / 4;
+        const int jb = warp * per, je = min(cn, jb + per);
+        for (int j = jb; j < je; j += 4) {
+            float s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int jj = min(j + u, je - 1);
+                const float4 *kr = reinterpret_cast<const float4 *>(Ks + jj * 32);
+                float a = 0.f;
+#pragma unroll
+                for (int d4 = 0; d4 < 8; ++d4) {
+                    const float4 kk = kr[d4];
+                    a = fmaf(qv[4 * d4], kk.x, a);
+                    a = fmaf(qv[4 * d4 + 1], kk.y, a);
+                    a = fmaf(qv[4 * d4 + 2], kk.z, a);
+                    a = fmaf(qv[4 * d4 + 3], kk.w, a);
+                }
+                s[u] = (j + u < je) ? a : -__int_as_float(0x7f800000);
+            }
+            const float mx = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+            const float corr = expf(m - mx);
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) acc[d] *= corr;
+            m = mx;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float pexp = expf(s[u] - mx);
+                l += pexp;
+                const int jj = min(j + u, je - 1);
+                const float4 *vr = reinterpret_cast<const float4 *>(Vs + jj * 32);
+#pragma unroll
+                for (int d4 = 0; d4 < 8; ++d4) {
+                    const float4 vv = vr[d4];
+                    acc[4 * d4] = fmaf(pexp, vv.x, acc[4 * d4]);
+                    acc[4 * d4 + 1] = fmaf(pexp, vv.y, acc[4 * d4 + 1]);
+                    acc[4 * d4 + 2] = fmaf(pexp, vv.z, acc[4 * d4 + 2]);
+                    acc[4 * d4 + 3] = fmaf(pexp, vv.w, acc[4 * d4 + 3]);
+                }
+            }
+        }
+    }
+    // merge the 4 key-slices
+    mb[warp][lane][32] = m;
+    mb[warp][lane][33] = l;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) mb[warp][lane][d] = acc[d];
+    __syncthreads();
+    float mm = mb[0][lane][32];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) mm = fmaxf(mm, mb[w][lane][32]);
+    float e[4], L = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        e[w] = expf(mb[w][lane][32] - mm);
+        L = fmaf(mb[w][lane][33], e[w], L);
+    }
+    if (qvalid) {
+        float *op = O + (size_t)(q0 + qi) * ldo + head * 32 + warp * 8;
+        float r[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) a = fmaf(mb[w][lane][warp * 8 + d], e[w], a);
+            r[d] = a / L;
+        }
+        *reinterpret_cast<float4 *>(op) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4 *>(op + 4) = make_float4(r[4], r[5], r[6], r[7]);
+    }
+}
+
+int attention_launch(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out, int ldo,
+                     const int *prob, int nprob, int maxLq, int M, int N, int mode, int heads, cudaStream_t st) {
+    if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
+    if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
+    const size_t smem = 2 * (size_t)ATT_KC * 32 * sizeof(float);
+    static thread_local bool configured = false;
+    if (!configured) {
+        DPM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((maxLq + 31) / 32, heads, nprob);
+    attention_kernel<<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
+    DPM_CHECK_LAUNCH();
+    return DPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// pairing: L2 normalise, dual softmax, global top-k   (decoder.py:180-192)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(float *__restrict__ X, int R, int C) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= R) return;
+    float *x = X + (size_t)row * C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) q = fmaf(x[c], x[c], q);
+    const float nrm = fmaxf(sqrtf(warp_sum(q)), 1e-12f);  // F.normalize eps
+    for (int c = lane; c < C; c += 32) x[c] = x[c] / nrm;
+}
+
+// per-row (max, sum exp) of S/tau; S (P, M, N)
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const float *__restrict__ S, int rows, int N, float tau, float2 *__restrict__ stats) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float *s = S + (size_t)row * N;
+    float mx = -__int_as_float(0x7f800000);
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, __fdiv_rn(s[j], tau));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) sum += expf(__fdiv_rn(s[j], tau) - mx);
+    sum = warp_sum(sum);
+    if (lane == 0) stats[row] = make_float2(mx, sum);
+}
+
+// per-column stats: block = 32 columns x 8 row-slices
+__global__ void __launch_bounds__(256)
+col_stats_kernel(const float *__restrict__ S, int M, int N, float tau, float2 *__restrict__ stats) {
+    __shared__ float smx[8][32], ssum[8][32];
+    const int p = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    const float *s = S + (size_t)p * M * N;
+    float mx = -__int_as_float(0x7f800000), sum = 0.f;
+    if (j < N) {
+        for (int i = ty; i < M; i += 8) mx = fmaxf(mx, __fdiv_rn(s[(size_t)i * N + j], tau));
+    }
+    smx[ty][tx] = mx;
+    __syncthreads();
+    float gm = smx[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) gm = fmaxf(gm, smx[w][tx]);
+    if (j < N) {
+        for (int i = ty; i < M; i += 8) sum += expf(__fdiv_rn(s[(size_t)i * N + j], tau) - gm);
+    }
+    ssum[ty][tx] = sum;
+    __syncthreads();
+    if (ty == 0 && j < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += ssum[w][tx];
+        stats[(size_t)p * N + j] = make_float2(gm, t);
+    }
+}
+
+// P = softmax_row * softmax_col, in place over S
+__global__ void __launch_bounds__(256)
+dual_softmax_kernel(float *__restrict__ S, int M, int N, float tau, const float2 *__restrict__ rs,
+                    const float2 *__restrict__ cs, long long total) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long row = t / N;
+    const int j = (int)(t % N);
+    const int p = (int)(row / M);
+    const float x = __fdiv_rn(S[t], tau);
+    const float2 r = rs[row], c = cs[(size_t)p * N + j];
+    S[t] = (expf(x - r.x) / r.y) * (expf(x - c.x) / c.y);
+}
+
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long *s, int n, int tid, int nthreads) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (n >> 1); i += nthreads) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = s[lo], b = s[hi];
+                if (desc ? (a < b) : (a > b)) { s[lo] = b; s[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// top-k of the flattened (M*N) non-negative matrix; order = (value desc, flat index asc).
+// One CTA per pair: 4-pass radix select of the k-th largest bit pattern, ordered collection,
+// bitonic sort of the k winners.
+constexpr int TOPK_T = 1024;
+constexpr int TOPK_MAXK = 4096;
+
+__global__ void __launch_bounds__(TOPK_T)
+topk_kernel(const float *__restrict__ Pm, int MN, int N, int k, int kp2, int32_t *__restrict__ si,
+            int32_t *__restrict__ di, float *__restrict__ conf) {
+    extern __shared__ __align__(16) unsigned char tk_smem[];
+    unsigned long long *sel = reinterpret_cast<unsigned long long *>(tk_smem);  // kp2
+    int *hist = reinterpret_cast<int *>(sel + kp2);                             // 32 x 256 (per-warp)
+    __shared__ unsigned s_prefix;
+    __shared__ int s_remaining, s_ngreater, s_eqbase, s_wcnt[32];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned *v = reinterpret_cast<const unsigned *>(Pm + (size_t)p * MN);
+    if (tid == 0) { s_prefix = 0u; s_remaining = k; s_ngreater = 0; s_eqbase = 0; }
+    for (int i = tid; i < kp2; i += TOPK_T) sel[i] = 0ull;
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < 32 * 256; i += TOPK_T) hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        for (int i0 = 0; i0 < MN; i0 += TOPK_T) {
+            const int i = i0 + tid;
+            const bool ok = i < MN && ((v[i] & himask) == prefix);
+            const unsigned digit = ok ? ((v[i] >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (ok && lane == __ffs(peers) - 1) hist[warp * 256 + digit] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        if (tid < 256) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += hist[w * 256 + tid];
+            hist[tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int cum = 0, rem = s_remaining, d = 255;
+            for (; d > 0; --d) {
+                if (cum + hist[d] >= rem) break;
+                cum += hist[d];
+            }
+            s_prefix = prefix | ((unsigned)d << shift);
+            s_remaining = rem - cum;
+        }
+        __syncthreads();
+    }
+    const unsigned T = s_prefix;
+    const int need_eq = s_remaining;  // how many of the == T elements are taken (lowest indices)
+    for (int i0 = 0; i0 < MN; i0 += TOPK_T) {
+        const int i = i0 + tid;
+        const unsigned u = i < MN ? v[i] : 0u;
+        const bool gt = i < MN && u > T;
+        const bool eq = i < MN && u == T;
+        if (gt) {
+            const int pos = atomicAdd(&s_ngreater, 1);
+            sel[pos] = ((unsigned long long)u << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+        }
+        if (__syncthreads_or(eq) && s_eqbase < need_eq) {
+            const unsigned bal = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) s_wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0;
+            for (int w = 0; w < warp; ++w) before += s_wcnt[w];
+            const int rank = s_eqbase + before + __popc(bal & ((1u << lane) - 1u));
+            if (eq && rank < need_eq)
+                sel[k - need_eq + rank] = ((unsigned long long)u << 32) | (unsigned)(0xffffffffu - (unsigned)i);
+            __syncthreads();
+            if (tid == 0) {
+                int t = 0;
+                for (int w = 0; w < 32; ++w) t += s_wcnt[w];
+                s_eqbase += t;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    bitonic_sort_desc(sel, kp2, tid, TOPK_T);
+    for (int r = tid; r < k; r += TOPK_T) {
+        const unsigned long long e = sel[r];
+        const unsigned flat = 0xffffffffu - (unsigned)e;
+        si[(size_t)p * k + r] = (int)(flat / (unsigned)N);
+        di[(size_t)p * k + r] = (int)(flat % (unsigned)N);
+        conf[(size_t)p * k + r] = __uint_as_float((unsigned)(e >> 32));
+    }
+}
+
+// rows of the offset head input: r < k: [F_src[i_r], F_dst[j_r]] ; k + r: [F_dst[j_r], F_src[i_r]]
+__global__ void __launch_bounds__(256)
+pair_gather_kernel(const float *__restrict__ F, int C, int M, int N, int k, const int32_t *__restrict__ si,
+                   const int32_t *__restrict__ di, float *__restrict__ X) {
+    const int p = blockIdx.y, r = blockIdx.x;  // r in [0, 2k)
+    const int rr = r < k ? r : r - k;
+    const size_t base = (size_t)p * (M + N);
+    const float *fs = F + (base + si[(size_t)p * k + rr]) * C;
+    const float *fd = F + (base + M + di[(size_t)p * k + rr]) * C;
+    float *x = X + ((size_t)p * 2 * k + r) * 2 * C;
+    const float *a = r < k ? fs : fd, *b = r < k ? fd : fs;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        x[c] = a[c];
+        x[C + c] = b[c];
+    }
+}
+
+// _get_corres_sets (decoder.py:202-225): 2k candidate correspondences, offset filter, ordered
+// compaction.  One CTA per pair.  out: src/dst (P,3,2k), w (P,2k), count (P).
+__global__ void __launch_bounds__(256)
+corres_kernel(const float4 *__restrict__ xyz, const float *__restrict__ off, const int32_t *__restrict__ si,
+              const int32_t *__restrict__ di, const float *__restrict__ conf, int M, int N, int k, float lim,
+              float *__restrict__ csrc, float *__restrict__ cdst, float *__restrict__ cw, int32_t *__restrict__ count) {
+    __shared__ int s_base, s_wcnt[8];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t base = (size_t)p * (M + N);
+    const int K2 = 2 * k;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < K2; r0 += 256) {
+        const int r = r0 + tid;
+        bool keep = false;
+        float3 s = make_float3(0.f, 0.f, 0.f), d = make_float3(0.f, 0.f, 0.f);
+        float w = 0.f;
+        if (r < K2) {
+            const int rr = r < k ? r : r - k;
+            const float4 xs = xyz[base + si[(size_t)p * k + rr]];
+            const float4 xd = xyz[base + M + di[(size_t)p * k + rr]];
+            const float *o = off + ((size_t)p * K2 + r) * 3;
+            const float ox = o[0], oy = o[1], oz = o[2];
+            keep = (ox * ox + oy * oy + oz * oz) <= lim;
+            if (r < k) { s = make_float3(xs.x + ox, xs.y + oy, xs.z + oz); d = make_float3(xd.x, xd.y, xd.z); }
+            else       { s = make_float3(xs.x, xs.y, xs.z); d = make_float3(xd.x + ox, xd.y + oy, xd.z + oz); }
+            w = conf[(size_t)p * k + rr];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_base;
+        for (int ww = 0; ww < warp; ++ww) before += s_wcnt[ww];
+        const int pos = before + __popc(bal & ((1u << lane) - 1u));
+        if (keep) {
+            float *ps = csrc + (size_t)p * 3 * K2, *pd = cdst + (size_t)p * 3 * K2;
+            ps[pos] = s.x; ps[K2 + pos] = s.y; ps[2 * K2 + pos] = s.z;
+            pd[pos] = d.x; pd[K2 + pos] = d.y; pd[2 * K2 + pos] = d.z;
+            cw[(size_t)p * K2 + pos] = w;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int ww = 0; ww < 8; ++ww) t += s_wcnt[ww];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) count[p] = s_base;
+}
+
+// ---------------------------------------------------------------------------------------
+// weighted Kabsch + 3-sigma loop (decoder.py:227-265).  One CTA per problem.
+// ---------------------------------------------------------------------------------------
+constexpr int KAB_T = 256;
+constexpr int KAB_MAX = 4096;
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *red /* [8][NV] */, int tid) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum_d(v[i]);
+    __syncthreads();
+    if ((tid & 31) == 0)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[(tid >> 5) * NV + i] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double t = 0.0;
+        for (int w = 0; w < KAB_T / 32; ++w) t += red[w * NV + i];
+        v[i] = t;
+    }
+}
+
+// one-sided Jacobi SVD of a 3x3 (fp64): A = U diag(s) V^T; returns R = V U^T
+__device__ void svd3_rot(const double S[9], double R[9]) {
+    double A[3][3], V[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { A[i][j] = S[3 * i + j]; V[i][j] = i == j ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double offmax = 0.0;
+        for (int pp = 0; pp < 2; ++pp)
+            for (int q = pp + 1; q < 3; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int i = 0; i < 3; ++i) { alpha += A[i][pp] * A[i][pp]; beta += A[i][q] * A[i][q]; gamma += A[i][pp] * A[i][q]; }
+                if (gamma == 0.0) continue;
+                const double rel = fabs(gamma) / sqrt(alpha * beta + 1e-300);
+                offmax = fmax(offmax, rel);
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = 0; i < 3; ++i) {
+                    const double ap = A[i][pp], aq = A[i][q];
+                    A[i][pp] = c * ap - s * aq; A[i][q] = s * ap + c * aq;
+                    const double vp = V[i][pp], vq = V[i][q];
+                    V[i][pp] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
+                }
+            }
+        if (offmax < 1e-15) break;
+    }
+    double U[3][3], sig[3];
+    for (int j = 0; j < 3; ++j) {
+        sig[j] = sqrt(A[0][j] * A[0][j] + A[1][j] * A[1][j] + A[2][j] * A[2][j]);
+    }
+    const double smax = fmax(sig[0], fmax(sig[1], sig[2]));
+    int bad = -1, nbad = 0;
+    for (int j = 0; j < 3; ++j) {
+        if (sig[j] > smax * 1e-14 && sig[j] > 0.0) {
+            for (int i = 0; i < 3; ++i) U[i][j] = A[i][j] / sig[j];
+        } else { bad = j; ++nbad; }
+    }
+    if (nbad == 1) {  // rank 2: complete U with the cross product of the other two columns
+        const int a = (bad + 1) % 3, b = (bad + 2) % 3;
+        U[0][bad] = U[1][a] * U[2][b] - U[2][a] * U[1][b];
+        U[1][bad] = U[2][a] * U[0][b] - U[0][a] * U[2][b];
+        U[2][bad] = U[0][a] * U[1][b] - U[1][a] * U[0][b];
+    } else if (nbad > 1) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) U[i][j] = V[i][j];  // degenerate: R = I
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = V[i][0] * U[j][0] + V[i][1] * U[j][1] + V[i][2] * U[j][2];
+}
+
+__global__ void __launch_bounds__(KAB_T)
+kabsch_kernel(const float *__restrict__ srcp, const float *__restrict__ dstp, const float *__restrict__ wp,
+              const int32_t *__restrict__ count, int ldk, float *__restrict__ result, uint8_t *__restrict__ inl_out,
+              float *__restrict__ conf_out) {
+    __shared__ unsigned long long skey[KAB_MAX];
+    float *serr = reinterpret_cast<float *>(skey);  // the sort keys are dead once the top-64 are marked
+    __shared__ uint8_t sinl[KAB_MAX];
+    __shared__ double red[8 * 16];
+    __shared__ float sRT[12];
+    __shared__ int s_flag[2], s_wcnt[8], s_base;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(count[p], min(ldk, KAB_MAX));
+    const float *sx = srcp + (size_t)p * 3 * ldk, *sy = sx + ldk, *sz = sy + ldk;
+    const float *dx = dstp + (size_t)p * 3 * ldk, *dy = dx + ldk, *dz = dy + ldk;
+    const float *w = wp + (size_t)p * ldk;
+    float *res = result + (size_t)p * DPM_REG_STRIDE;
+
+    // initial inliers: w > 0.5, plus the 64 largest weights (ties: lowest index)
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    if (np2 < 2) np2 = 2;
+    for (int i = tid; i < np2; i += KAB_T)
+        skey[i] = i < n ? (((unsigned long long)__float_as_uint(fmaxf(w[i], 0.f)) << 32) | (unsigned)(0xffffffffu - (unsigned)i)) : 0ull;
+    for (int i = tid; i < n; i += KAB_T) sinl[i] = w[i] > 0.5f;
+    __syncthreads();
+    bitonic_sort_desc(skey, np2, tid, KAB_T);
+    if (tid < 64 && tid < n) sinl[0xffffffffu - (unsigned)skey[tid]] = 1;
+    __syncthreads();
+
+    int iters = 0;
+    float rmse = 0.f;
+    while (true) {
+        double a[16];
+        for (int i = 0; i < 16; ++i) a[i] = 0.0;
+        for (int i = tid; i < n; i += KAB_T)
+            if (sinl[i]) {
+                const double wi = w[i];
+                a[0] += wi;
+                a[1] += wi * sx[i]; a[2] += wi * sy[i]; a[3] += wi * sz[i];
+                a[4] += wi * dx[i]; a[5] += wi * dy[i]; a[6] += wi * dz[i];
+            }
+        block_sum<7>(reinterpret_cast<double(&)[7]>(a), red, tid);
+        const float wsum = (float)a[0];
+        const float csx = (float)a[1] / wsum, csy = (float)a[2] / wsum, csz = (float)a[3] / wsum;
+        const float cdx = (float)a[4] / wsum, cdy = (float)a[5] / wsum, cdz = (float)a[6] / wsum;
+        double h[9];
+        for (int i = 0; i < 9; ++i) h[i] = 0.0;
+        for (int i = tid; i < n; i += KAB_T)
+            if (sinl[i]) {
+                const float ax = sx[i] - csx, ay = sy[i] - csy, az = sz[i] - csz;
+                const float bx = dx[i] - cdx, by = dy[i] - cdy, bz = dz[i] - cdz;
+                const double wi = w[i];
+                h[0] += wi * ax * bx; h[1] += wi * ax * by; h[2] += wi * ax * bz;
+                h[3] += wi * ay * bx; h[4] += wi * ay * by; h[5] += wi * ay * bz;
+                h[6] += wi * az * bx; h[7] += wi * az * by; h[8] += wi * az * bz;
+            }
+        block_sum<9>(h, red, tid);
+        if (tid == 0) {
+            double Sm[9], R[9];
+            for (int i = 0; i < 9; ++i) Sm[i] = (double)(float)h[i];  // the reference forms S in fp32, then .double()
+            svd3_rot(Sm, R);
+            const double cs[3] = {csx, csy, csz}, cd[3] = {cdx, cdy, cdz};
+            for (int i = 0; i < 3; ++i) {
+                const double t = cd[i] - (R[3 * i] * cs[0] + R[3 * i + 1] * cs[1] + R[3 * i + 2] * cs[2]);
+                sRT[9 + i] = (float)t;
+            }
+            for (int i = 0; i < 9; ++i) sRT[i] = (float)R[i];
+        }
+        __syncthreads();
+        float R[9], T[3];
+        for (int i = 0; i < 9; ++i) R[i] = sRT[i];
+        for (int i = 0; i < 3; ++i) T[i] = sRT[9 + i];
+        double e[2] = {0.0, 0.0};
+        int cnt = 0;
+        for (int i = tid; i < n; i += KAB_T) {
+            const float ex = R[0] * sx[i] + R[1] * sy[i] + R[2] * sz[i] + T[0] - dx[i];
+            const float ey = R[3] * sx[i] + R[4] * sy[i] + R[5] * sz[i] + T[1] - dy[i];
+            const float ez = R[6] * sx[i] + R[7] * sy[i] + R[8] * sz[i] + T[2] - dz[i];
+            const float er = sqrtf(ex * ex + ey * ey + ez * ez);
+            serr[i] = er;
+            if (sinl[i]) { e[0] += er; ++cnt; }
+        }
+        e[1] = (double)cnt;
+        block_sum<2>(e, red, tid);
+        const double ninl = e[1];
+        const float mean = (float)(e[0] / ninl);
+        double v[1] = {0.0};
+        for (int i = tid; i < n; i += KAB_T)
+            if (sinl[i]) { const double dd = (double)serr[i] - (double)mean; v[0] += dd * dd; }
+        block_sum<1>(v, red, tid);
+        const float stdv = (float)sqrt(v[0] / (ninl - 1.0));  // unbiased; NaN when ninl <= 1, as torch.std
+        const float thr = mean + 3.0f * stdv;
+        if (tid < 2) s_flag[tid] = 0;
+        __syncthreads();
+        int changed = 0, newcnt = 0;
+        for (int i = tid; i < n; i += KAB_T) {
+            const uint8_t ni = serr[i] <= thr ? 1 : 0;  // false for NaN thr
+            changed |= (ni != sinl[i]);
+            newcnt += ni;
+            sinl[i] = ni;
+        }
+        if (changed) atomicOr(&s_flag[0], 1);
+        if (newcnt) atomicAdd(&s_flag[1], newcnt);
+        __syncthreads();
+        ++iters;
+        const bool stop = iters >= 3 || s_flag[0] == 0 || s_flag[1] < 30;
+        const int nfinal = s_flag[1];
+        __syncthreads();
+        if (stop) {
+            double q[1] = {0.0};
+            for (int i = tid; i < n; i += KAB_T)
+                if (sinl[i]) q[0] += (double)serr[i] * (double)serr[i];
+            block_sum<1>(q, red, tid);
+            rmse = (float)sqrt(q[0] / (double)nfinal);
+            if (tid == 0) {
+                for (int i = 0; i < 9; ++i) res[DPM_REG_R + i] = R[i];
+                for (int i = 0; i < 3; ++i) res[DPM_REG_T + i] = T[i];
+                res[DPM_REG_RMSE] = rmse;
+                res[DPM_REG_NCORR] = (float)n;
+                res[DPM_REG_NINLIER] = (float)nfinal;
+                res[DPM_REG_ITERS] = (float)iters;
+            }
+            break;
+        }
+    }
+    // inlier mask + ordered compaction of the inlier confidences
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < ldk; r0 += KAB_T) {
+        const int i = r0 + tid;
+        const bool in = i < n && sinl[i];
+        if (inl_out && i < ldk) inl_out[(size_t)p * ldk + i] = in ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_base;
+        for (int ww = 0; ww < warp; ++ww) before += s_wcnt[ww];
+        if (in && conf_out) conf_out[(size_t)p * ldk + before + __popc(bal & ((1u << lane) - 1u))] = w[i];
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int ww = 0; ww < 8; ++ww) t += s_wcnt[ww];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+}
+
+int kabsch_launch(const float *src, const float *dst, const float *w, const int32_t *count, int P, int ldk,
+                  float *result, uint8_t *inlier, float *conf_out, cudaStream_t st) {
+    if (P <= 0 || ldk <= 0) return fail(DPM_ERR_SHAPE, "kabsch: bad shape");
+    if (ldk > KAB_MAX) return fail(DPM_ERR_UNSUPPORTED, "kabsch: %d correspondences exceed the limit %d", ldk, KAB_MAX);
+    kabsch_kernel<<<P, KAB_T, 0, st>>>(src, dst, w, count, ldk, result, inlier, conf_out);
+    DPM_CHECK_LAUNCH();
+    return DPM_OK;
+}
+
+// mean over the tokens of each (pair, side) -> (P, 2C) = [mean src ; mean dst]   (heads.py:64-67)
+__global__ void __launch_bounds__(256)
+token_mean_kernel(const float *__restrict__ X, int C, int M, int N, float *__restrict__ out) {
+    const int p = blockIdx.x, side = blockIdx.y;
+    const int L = side ? N : M;
+    const float *x = X + ((size_t)p * (M + N) + (side ? M : 0)) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s += x[(size_t)l * C + c];
+        out[(size_t)p * 2 * C + side * C + c] = s / (float)L;
+    }
+}
+
+__global__ void sigmoid_kernel(const float *__restrict__ x, float *__restrict__ y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 1.0f / (1.0f + expf(-x[i]));
+}
+
+// ---------------------------------------------------------------------------------------
+// pipelines
+// ---------------------------------------------------------------------------------------
+static int dec_num_weights(const dpm_decoder_desc *d) { return 2 + d->attention_layers * 18 + 4 + 10 + 8 + 4; }
+
+struct DecW {
+    const float *proj_w, *proj_b;
+    struct Layer {
+        const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *ca_in_w, *ca_in_b, *ca_out_w, *ca_out_b;
+        const float *m0_w, *m0_b, *m2_w, *m2_b, *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b;
+    } layer[16];
+    const float *sim0_w, *sim0_b, *sim2_w, *sim2_b;
+    const float *off0_w, *off0_b, *off2_w, *off2_b, *off4_w, *off4_b, *offd_w, *offd_b, *offh_w, *offh_b;
+    const float *lp0_w, *lp0_b, *lp2_w, *lp2_b, *lq0_w, *lq0_b, *lq2_w, *lq2_b;
+    const float *dim_t;  // extra (last) entry: positional-embedding frequencies
+};
+
+static void dec_bind(const dpm_decoder_desc *d, const float *const *w, DecW &o) {
+    int i = 0;
+    o.proj_w = w[i++]; o.proj_b = w[i++];
+    for (int l = 0; l < d->attention_layers; ++l) {
+        DecW::Layer &L = o.layer[l];
+        L.sa_in_w = w[i++]; L.sa_in_b = w[i++]; L.sa_out_w = w[i++]; L.sa_out_b = w[i++];
+        L.ca_in_w = w[i++]; L.ca_in_b = w[i++]; L.ca_out_w = w[i++]; L.ca_out_b = w[i++];
+        L.m0_w = w[i++]; L.m0_b = w[i++]; L.m2_w = w[i++]; L.m2_b = w[i++];
+        L.n1_w = w[i++]; L.n1_b = w[i++]; L.n2_w = w[i++]; L.n2_b = w[i++]; L.n3_w = w[i++]; L.n3_b = w[i++];
+    }
+    o.sim0_w = w[i++]; o.sim0_b = w[i++]; o.sim2_w = w[i++]; o.sim2_b = w[i++];
+    o.off0_w = w[i++]; o.off0_b = w[i++]; o.off2_w = w[i++]; o.off2_b = w[i++]; o.off4_w = w[i++]; o.off4_b = w[i++];
+    o.offd_w = w[i++]; o.offd_b = w[i++]; o.offh_w = w[i++]; o.offh_b = w[i++];
+    o.lp0_w = w[i++]; o.lp0_b = w[i++]; o.lp2_w = w[i++]; o.lp2_b = w[i++];
+    o.lq0_w = w[i++]; o.lq0_b = w[i++]; o.lq2_w = w[i++]; o.lq2_b = w[i++];
+    i += 4;  // coarse_pairing_head: training only (decoder.py:46-49)
+    o.dim_t = w[i++];
+}
+
+// _descriptor_attention_forward (decoder.py:145-162): -> F (R, C) correlated features, xyz (R)
+static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float *src, const float *dst, int P, int M,
+                           int N, Arena &a, float **F_out, float4 **xyz_out, cudaStream_t st) {
+    const bool dry = a.dry;
+    const int C = d->model_channel, Cf = d->in_channel, H = d->heads;
+    const int R = P * (M + N);
+    if (C != H * 32) return fail(DPM_ERR_UNSUPPORTED, "decoder: head_dim must be 32 (model_channel=%d heads=%d)", C, H);
+    if (d->attention_layers < 0 || d->attention_layers > 16) return fail(DPM_ERR_SHAPE, "decoder: attention_layers");
+    float *fea = a.get<float>((size_t)R * Cf);
+    float4 *xyz = a.get<float4>((size_t)R);
+    float *pos = a.get<float>((size_t)R * C);
+    float *x = a.get<float>((size_t)R * C);
+    float *y = a.get<float>((size_t)R * C);
+    float *qkv = a.get<float>((size_t)R * 3 * C);
+    float *att = a.get<float>((size_t)R * C);
+    if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "decoder: workspace too small");
+    *F_out = x;
+    *xyz_out = xyz;
+    if (dry) return DPM_OK;
+    const int npf = C / 3 / 2 * 2;
+    const int maxL = M > N ? M : N;
+    dim3 g((maxL + 31) / 32, (Cf + 31) / 32, 2 * P);
+    dec_unpack_kernel<<<g, 256, 0, st>>>(src, dst, M, N, Cf, fea, xyz);
+    DPM_CHECK_LAUNCH();
+    DPM_TRY(posenc_launch(reinterpret_cast<const float *>(xyz), 4, w.dim_t, npf, pos, R, C, st));
+    // x = projection(fea) + pos   (the "+ pos" of the first layer, descriptor_attention.py:31)
+    DPM_TRY(linear_launch(fea, Cf, w.proj_w, Cf, w.proj_b, pos, C, x, C, R, C, Cf, DPM_ACT_NONE, st));
+    for (int l = 0; l < d->attention_layers; ++l) {
+        const DecW::Layer &L = w.layer[l];
+        const bool last = l == d->attention_layers - 1;
+        // self attention (shared weights for src and dst), add & norm1, then "+ pos" again
+        DPM_TRY(linear_launch(x, C, L.sa_in_w, C, L.sa_in_b, nullptr, 0, qkv, 3 * C, R, 3 * C, C, DPM_ACT_NONE, st));
+        DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 0, H, st));
+        DPM_TRY(linear_launch(att, C, L.sa_out_w, C, L.sa_out_b, x, C, y, C, R, C, C, DPM_ACT_NONE, st));
+        DPM_TRY(layernorm_launch(y, C, L.n1_w, L.n1_b, pos, C, x, C, R, C, DPM_ACT_NONE, st));
+        // cross attention both ways, add & norm2
+        DPM_TRY(linear_launch(x, C, L.ca_in_w, C, L.ca_in_b, nullptr, 0, qkv, 3 * C, R, 3 * C, C, DPM_ACT_NONE, st));
+        DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 1, H, st));
+        DPM_TRY(linear_launch(att, C, L.ca_out_w, C, L.ca_out_b, x, C, y, C, R, C, C, DPM_ACT_NONE, st));
+        DPM_TRY(layernorm_launch(y, C, L.n2_w, L.n2_b, nullptr, 0, x, C, R, C, DPM_ACT_NONE, st));
+        // mlp, add & norm3 (+ pos for the next layer)
+        DPM_TRY(linear_launch(x, C, L.m0_w, C, L.m0_b, nullptr, 0, att, C, R, C, C, DPM_ACT_RELU, st));
+        DPM_TRY(linear_launch(att, C, L.m2_w, C, L.m2_b, x, C, y, C, R, C, C, DPM_ACT_NONE, st));
+        DPM_TRY(layernorm_launch(y, C, L.n3_w, L.n3_b, last ? nullptr : pos, C, x, C, R, C, DPM_ACT_NONE, st));
+    }
+    return DPM_OK;
+}
+
+static int registration_run(const dpm_decoder_desc *d, const float *const *weights, const float *src,
+                            const float *dst, int P, int M, int N, int k, float *result, float *conf_out, Arena &a,
+                            cudaStream_t st) {
+    const bool dry = a.dry;
+    if (P <= 0 || M <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "registration: bad shape P=%d M=%d N=%d", P, M, N);
+    if (k <= 0 || (long long)k > (long long)M * N) return fail(DPM_ERR_SHAPE, "registration: k=%d pairs out of range", k);
+    if (k > TOPK_MAXK || 2 * k > KAB_MAX) return fail(DPM_ERR_UNSUPPORTED, "registration: k=%d exceeds the limit %d", k, KAB_MAX / 2);
+    DecW w;
+    if (!dry) dec_bind(d, weights, w);
+    const int C = d->model_channel, R = P * (M + N), K2 = 2 * k;
+    float *F = nullptr;
+    float4 *xyz = nullptr;
+    DPM_TRY(attention_stack(d, w, src, dst, P, M, N, a, &F, &xyz, st));
+    float *h = a.get<float>((size_t)R * C);
+    float *sim = a.get<float>((size_t)R * C);
+    float *S = a.get<float>((size_t)P * M * N);
+    float2 *rs = a.get<float2>((size_t)P * M);
+    float2 *cs = a.get<float2>((size_t)P * N);
+    int32_t *si = a.get<int32_t>((size_t)P * k);
+    int32_t *di = a.get<int32_t>((size_t)P * k);
+    float *conf = a.get<float>((size_t)P * k);
+    float *X = a.get<float>((size_t)P * K2 * 2 * C);
+    float *o1 = a.get<float>((size_t)P * K2 * C);
+    float *o2 = a.get<float>((size_t)P * K2 * (C / 2));
+    float *oi = a.get<float>((size_t)P * K2 * (C / 4));
+    float *o3 = a.get<float>((size_t)P * K2 * (C / 4));
+    float *off = a.get<float>((size_t)P * K2 * 3);
+    float *csrc = a.get<float>((size_t)P * 3 * K2);
+    float *cdst = a.get<float>((size_t)P * 3 * K2);
+    float *cw = a.get<float>((size_t)P * K2);
+    int32_t *cnt = a.get<int32_t>((size_t)P);
+    if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "registration: workspace too small");
+    if (dry) return DPM_OK;
+
+    // similarity head + L2 normalise (decoder.py:181-185)
+    DPM_TRY(linear_launch(F, C, w.sim0_w, C, w.sim0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
+    DPM_TRY(linear_launch(h, C, w.sim2_w, C, w.sim2_b, nullptr, 0, sim, C, R, C, C, DPM_ACT_NONE, st));
+    l2norm_rows_kernel<<<(R + 7) / 8, 256, 0, st>>>(sim, R, C);
+    DPM_CHECK_LAUNCH();
+    // S_p = A_src . A_dst^T
+    DPM_TRY(linear_batched_launch(sim, C, (long long)(M + N) * C, sim + (size_t)M * C, C, (long long)(M + N) * C, nullptr,
+                                  nullptr, 0, S, N, (long long)M * N, M, N, C, P, DPM_ACT_NONE, st));
+    row_stats_kernel<<<(P * M + 7) / 8, 256, 0, st>>>(S, P * M, N, d->tau, rs);
+    DPM_CHECK_LAUNCH();
+    col_stats_kernel<<<dim3((N + 31) / 32, P, 1), 256, 0, st>>>(S, M, N, d->tau, cs);
+    DPM_CHECK_LAUNCH();
+    const long long total = (long long)P * M * N;
+    dual_softmax_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, M, N, d->tau, rs, cs, total);
+    DPM_CHECK_LAUNCH();
+    int kp2 = 2;
+    while (kp2 < k) kp2 <<= 1;
+    const size_t tk_smem = (size_t)kp2 * 8 + 32 * 256 * 4;
+    static thread_local bool configured = false;
+    if (!configured) {
+        DPM_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(TOPK_MAXK * 8 + 32 * 256 * 4)));
+        configured = true;
+    }
+    topk_kernel<<<P, TOPK_T, tk_smem, st>>>(S, M * N, N, k, kp2, si, di, conf);
+    DPM_CHECK_LAUNCH();
+    // offset head on [f_s;f_d] and [f_d;f_s]  (heads.py:22-42)
+    pair_gather_kernel<<<dim3(K2, P, 1), 256, 0, st>>>(F, C, M, N, k, si, di, X);
+    DPM_CHECK_LAUNCH();
+    const int RO = P * K2;
+    DPM_TRY(linear_launch(X, 2 * C, w.off0_w, 2 * C, w.off0_b, nullptr, 0, o1, C, RO, C, 2 * C, DPM_ACT_RELU, st));
+    DPM_TRY(linear_launch(o1, C, w.off2_w, C, w.off2_b, nullptr, 0, o2, C / 2, RO, C / 2, C, DPM_ACT_RELU, st));
+    DPM_TRY(linear_launch(X, 2 * C, w.offd_w, 2 * C, w.offd_b, nullptr, 0, oi, C / 4, RO, C / 4, 2 * C, DPM_ACT_NONE, st));
+    DPM_TRY(linear_launch(o2, C / 2, w.off4_w, C / 2, w.off4_b, oi, C / 4, o3, C / 4, RO, C / 4, C / 2, DPM_ACT_RELU, st));
+    DPM_TRY(linear_launch(o3, C / 4, w.offh_w, C / 4, w.offh_b, nullptr, 0, off, 3, RO, 3, C / 4, DPM_ACT_NONE, st));
+    corres_kernel<<<P, 256, 0, st>>>(xyz, off, si, di, conf, M, N, k, d->eps_offset * d->eps_offset, csrc, cdst, cw, cnt);
+    DPM_CHECK_LAUNCH();
+    DPM_TRY(kabsch_launch(csrc, cdst, cw, cnt, P, K2, result, nullptr, conf_out, st));
+    return DPM_OK;
+}
+
+static int loop_run(const dpm_decoder_desc *d, const float *const *weights, const float *src, const float *dst, int P,
+                    int M, int N, float *prob, Arena &a, cudaStream_t st) {
+    const bool dry = a.dry;
+    if (P <= 0 || M <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "loop_detection: bad shape");
+    DecW w;
+    if (!dry) dec_bind(d, weights, w);
+    const int C = d->model_channel, R = P * (M + N);
+    float *F = nullptr;
+    float4 *xyz = nullptr;
+    DPM_TRY(attention_stack(d, w, src, dst, P, M, N, a, &F, &xyz, st));
+    float *h = a.get<float>((size_t)R * C);
+    float *g = a.get<float>((size_t)R * C);
+    float *mean = a.get<float>((size_t)P * 2 * C);
+    float *p1 = a.get<float>((size_t)P * 2 * C);
+    float *logit = a.get<float>((size_t)P);
+    if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "loop_detection: workspace too small");
+    if (dry) return DPM_OK;
+    DPM_TRY(linear_launch(F, C, w.lp0_w, C, w.lp0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
+    DPM_TRY(linear_launch(h, C, w.lp2_w, C, w.lp2_b, nullptr, 0, g, C, R, C, C, DPM_ACT_NONE, st));
+    token_mean_kernel<<<dim3(P, 2, 1), 256, 0, st>>>(g, C, M, N, mean);
+    DPM_CHECK_LAUNCH();
+    DPM_TRY(linear_launch(mean, 2 * C, w.lq0_w, 2 * C, w.lq0_b, nullptr, 0, p1, 2 * C, P, 2 * C, 2 * C, DPM_ACT_RELU, st));
+    DPM_TRY(linear_launch(p1, 2 * C, w.lq2_w, 2 * C, w.lq2_b, nullptr, 0, logit, 1, P, 1, 2 * C, DPM_ACT_NONE, st));
+    sigmoid_kernel<<<(P + 127) / 128, 128, 0, st>>>(logit, prob, P);
+    DPM_CHECK_LAUNCH();
+    return DPM_OK;
+}
+
+}  // namespace dpm
+
+using namespace dpm;
+
+/* weights = the decoder state_dict tensors in state_dict order PLUS one trailing entry:
+ * dim_t (model_channel/3/2*2 floats), the positional-embedding frequencies. */
+extern "C" int dpm_decoder_num_weights(const dpm_decoder_desc *desc) { return desc ? dec_num_weights(desc) + 1 : 0; }
+
+extern "C" size_t dpm_registration_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N, int k) {
+    if (!desc) return 0;
+    Arena a(nullptr, 0);
+    if (registration_run(desc, nullptr, nullptr, nullptr, P, M, N, k, nullptr, nullptr, a, nullptr) != DPM_OK) return 0;
+    // loop detection shares the attention stack; its extra buffers are smaller than registration's
+    return a.off + 256;
+}
+
+extern "C" int dpm_registration_forward(const dpm_decoder_desc *desc, const float *const *weights, int n_weights,
+                                        const float *src, const float *dst, int P, int M, int N, int k, float *result,
+                                        float *conf_out, void *ws, size_t ws_bytes, dpm_stream_t stream) {
+    if (!desc || !weights || !src || !dst || !result || !conf_out || !ws) return fail(DPM_ERR_ARG, "registration: null pointer");
+    if (n_weights != dec_num_weights(desc) + 1)
+        return fail(DPM_ERR_SHAPE, "registration: got %d weight tensors, expected %d", n_weights, dec_num_weights(desc) + 1);
+    Arena a(ws, ws_bytes);
+    return registration_run(desc, weights, src, dst, P, M, N, k, result, conf_out, a, (cudaStream_t)stream);
+}
+
+extern "C" size_t dpm_loop_detection_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N) {
+    if (!desc) return 0;
+    Arena a(nullptr, 0);
+    if (loop_run(desc, nullptr, nullptr, nullptr, P, M, N, nullptr, a, nullptr) != DPM_OK) return 0;
+    return a.off + 256;
+}
+
+extern "C" int dpm_loop_detection_forward(const dpm_decoder_desc *desc, const float *const *weights, int n_weights,
+                                          const float *src, const float *dst, int P, int M, int N, float *prob,
+                                          void *ws, size_t ws_bytes, dpm_stream_t stream) {
+    if (!desc || !weights || !src || !dst || !prob || !ws) return fail(DPM_ERR_ARG, "loop_detection: null pointer");
+    if (n_weights != dec_num_weights(desc) + 1)
+        return fail(DPM_ERR_SHAPE, "loop_detection: got %d weight tensors, expected %d", n_weights, dec_num_weights(desc) + 1);
+    Arena a(ws, ws_bytes);
+    return loop_run(desc, weights, src, dst, P, M, N, prob, a, (cudaStream_t)stream);
+}
+
+extern "C" int dpm_posenc_f32(const float *xyz, int ldx, const float *dim_t, int npf, float *emb, int R, int C,
+                              dpm_stream_t stream) {
+    if (!xyz || !dim_t || !emb) return fail(DPM_ERR_ARG, "posenc: null pointer");
+    return posenc_launch(xyz, ldx, dim_t, npf, emb, R, C, (cudaStream_t)stream);
+}
+
+extern "C" int dpm_attention_f32(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
+                                 int ldo, const int *prob, int nprob, int max_lq, int heads, dpm_stream_t stream) {
+    if (!q || !k || !v || !out || !prob) return fail(DPM_ERR_ARG, "attention: null pointer");
+    return attention_launch(q, ldq, k, ldk, v, ldv, out, ldo, prob, nprob, max_lq, 0, 0, 0, heads, (cudaStream_t)stream);
+}
+
+extern "C" int dpm_kabsch_f32(const float *src, const float *dst, const float *w, const int32_t *count, int P, int ldk,
+                              float *result, uint8_t *inlier, float *conf_out, dpm_stream_t stream) {
+    if (!src || !dst || !w || !count || !result) return fail(DPM_ERR_ARG, "kabsch: null pointer");
+    return kabsch_launch(src, dst, w, count, P, ldk, result, inlier, conf_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,303 @@
+// encoder.cu -- Encoder.forward (network/encoder/encoder.py:51-69) as one native call:
+// the whole PointNeXt backbone + FPN is enqueued on the caller's stream from C++ (no
+// Python between kernels, no host sync, CUDA-graph capturable).
+//
+// Internal layout: points are rows.  Coordinates live as float4 (x,y,z,0) so every access is
+// one aligned 16-byte load; features are (B, N, C) row-major so a gathered neighbour is one
+// contiguous row.  Channel-first tensors exist only at the API boundary.
+#include "common.cuh"
+
+namespace dpm {
+
+// points (B,C,N) channel-first -> xyz4 (B,N) + stem features F0 (B,N,width) = W0 . p[:cin] + b0
+// (Conv1d 3->16, encoder.py:53)
+__global__ void __launch_bounds__(256)
+prep_kernel(const float *__restrict__ points, int C, int N, int cin, const float *__restrict__ W0,
+            const float *__restrict__ b0, int width, float4 *__restrict__ xyz4, float *__restrict__ F0) {
+    const int b = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float *p = points + (size_t)b * C * N + n;
+    float in[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) in[c] = c < cin ? p[(size_t)c * N] : 0.f;
+    const float x = p[0], y = p[(size_t)N], z = p[(size_t)2 * N];
+    xyz4[(size_t)b * N + n] = make_float4(x, y, z, 0.f);
+    float *f = F0 + ((size_t)b * N + n) * width;
+    for (int o = 0; o < width; ++o) {
+        float acc = b0 ? b0[o] : 0.f;
+        for (int c = 0; c < cin; ++c) acc = fmaf(W0[o * cin + c], in[c], acc);
+        f[o] = acc;
+    }
+}
+
+// lengths = (~padding).sum(1)  (network/encoder/utils.py:94,115,212,278)
+__global__ void __launch_bounds__(256) pad_to_len_kernel(const uint8_t *__restrict__ pad, int N, int *__restrict__ len32) {
+    const int b = blockIdx.x;
+    int c = 0;
+    if (pad) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) c += pad[(size_t)b * N + i] ? 0 : 1;
+    } else {
+        c = threadIdx.x == 0 ? N : 0;
+    }
+    __shared__ int red[8];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        len32[b] = t;
+    }
+}
+
+// (B,S,C) rows -> channel-first outputs: fea (B,C,S), coor (B,3,S), pad, descriptors
+// (B,C+3,S) = [fea ; xyz*scale]  (odometry.py:46-49)
+__global__ void __launch_bounds__(256)
+emit_kernel(const float *__restrict__ fea, const float4 *__restrict__ xyz4, const uint8_t *__restrict__ pad, int S,
+            int C, float scale, float *__restrict__ out_coor, float *__restrict__ out_fea,
+            uint8_t *__restrict__ out_pad, float *__restrict__ desc) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int s = s0 + r, c = c0 + tx;
+        tile[r][tx] = (s < S && c < C) ? fea[((size_t)b * S + s) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, s = s0 + tx;
+        if (c < C && s < S) {
+            const float v = tile[tx][r];
+            if (out_fea) out_fea[((size_t)b * C + c) * S + s] = v;
+            if (desc) desc[((size_t)b * (C + 3) + c) * S + s] = v;
+        }
+    }
+    if (blockIdx.y == 0 && ty == 0) {
+        const int s = s0 + tx;
+        if (s < S) {
+            const float4 p = xyz4[(size_t)b * S + s];
+            if (out_coor) {
+                out_coor[((size_t)b * 3 + 0) * S + s] = p.x;
+                out_coor[((size_t)b * 3 + 1) * S + s] = p.y;
+                out_coor[((size_t)b * 3 + 2) * S + s] = p.z;
+            }
+            if (desc) {
+                desc[((size_t)b * (C + 3) + C + 0) * S + s] = p.x * scale;
+                desc[((size_t)b * (C + 3) + C + 1) * S + s] = p.y * scale;
+                desc[((size_t)b * (C + 3) + C + 2) * S + s] = p.z * scale;
+            }
+            if (out_pad) out_pad[(size_t)b * S + s] = pad ? pad[(size_t)b * S + s] : 0;
+        }
+    }
+}
+
+struct Level {
+    float4 *xyz;
+    float *fea;
+    uint8_t *pad;
+    int *len;
+    int n, c;
+};
+
+static int enc_num_weights(const dpm_encoder_desc *d) {
+    int n = 2;
+    for (int i = 0; i < d->n_stages; ++i) n += 4 + (d->n_blocks[i] - 1) * 12;
+    n += d->upsample_layers * 8;
+    return n;
+}
+
+// One code path for sizing (dry arena, no launches) and for running.
+static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_weights, const float *points, int C,
+                       const uint8_t *padding, int B, int N, float *out_coor, float *out_fea, uint8_t *out_pad,
+                       float *desc_out, float coor_scale, int64_t *trace_fps, int32_t *trace_knn, Arena &a,
+                       cudaStream_t st) {
+    const bool dry = a.dry;
+    if (d->n_stages < 1 || d->n_stages > DPM_MAX_STAGES) return fail(DPM_ERR_SHAPE, "encoder: n_stages=%d", d->n_stages);
+    if (d->in_channel < 1 || d->in_channel > 8 || C < 3 || d->in_channel > C)
+        return fail(DPM_ERR_SHAPE, "encoder: in_channel=%d with C=%d", d->in_channel, C);
+    if (d->upsample_layers < 0 || d->upsample_layers > d->n_stages) return fail(DPM_ERR_SHAPE, "encoder: upsample_layers");
+    if (!dry && n_weights != enc_num_weights(d))
+        return fail(DPM_ERR_SHAPE, "encoder: got %d weight tensors, expected %d", n_weights, enc_num_weights(d));
+    for (int i = 0; i < d->n_stages; ++i)
+        if (d->n_blocks[i] < 1 || d->n_blocks[i] > DPM_MAX_BLOCKS) return fail(DPM_ERR_SHAPE, "encoder: n_blocks[%d]", i);
+
+    int wi = 0;
+    auto W = [&](void) -> const float * { return dry ? nullptr : w[wi++]; };
+
+    Level lv[DPM_MAX_STAGES + 1 + DPM_MAX_STAGES];
+    int nl = 0;
+    // level 0
+    Level &l0 = lv[nl++];
+    l0.n = N;
+    l0.c = d->width;
+    l0.xyz = a.get<float4>((size_t)B * N);
+    l0.fea = a.get<float>((size_t)B * N * d->width);
+    l0.len = a.get<int>(B);
+    l0.pad = nullptr;  // level-0 padding is the caller's tensor
+    const float *W0 = W(), *b0 = W();
+    if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
+    if (!dry) {
+        pad_to_len_kernel<<<B, 256, 0, st>>>(padding, N, l0.len);
+        DPM_CHECK_LAUNCH();
+        dim3 g((N + 255) / 256, B, 1);
+        prep_kernel<<<g, 256, 0, st>>>(points, C, N, d->in_channel, W0, b0, d->width, l0.xyz, l0.fea);
+        DPM_CHECK_LAUNCH();
+    }
+
+    size_t fps_off = 0, knn_off = 0;
+    int width = d->width;
+    for (int i = 0; i < d->n_stages; ++i) {
+        const Level src = lv[nl - 1];
+        const int S = d->npoint[i], Cin = width, Cout = 2 * width;
+        if (S <= 0) return fail(DPM_ERR_SHAPE, "encoder: npoint[%d]=%d", i, S);
+        Level &dst = lv[nl++];
+        dst.n = S;
+        dst.c = Cout;
+        dst.xyz = a.get<float4>((size_t)B * S);
+        dst.pad = a.get<uint8_t>((size_t)B * S);
+        dst.len = a.get<int>(B);
+        dst.fea = a.get<float>((size_t)B * S * Cout);
+        // --- set abstraction (pointnext.py:38-64) ---
+        const int K0 = d->nsample[i][0];
+        const double r0 = d->radius[i][0];
+        int32_t *gidx = a.get<int32_t>((size_t)B * S * K0);
+        float *Z = a.get<float>((size_t)B * src.n * Cout);
+        const float *Wsa = W(), *bsa = W(), *gsa = W(), *besa = W();
+        if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
+        if (!dry) {
+            DPM_TRY(fps_launch(src.xyz, B, src.n, src.len, S, trace_fps ? trace_fps + fps_off : nullptr, nullptr, dst.xyz,
+                               dst.pad, dst.len, st));
+            const float r2 = (float)(r0 * r0);  // fp32(radius ** 2), utils.py:119
+            DPM_TRY(knn_launch(dst.xyz, src.xyz, B, S, src.n, nullptr, src.len, K0, r2, KNN_MODE_HYBRID, nullptr, gidx,
+                               nullptr, st));
+            if (trace_knn) {
+                DPM_CHECK_CUDA(cudaMemcpyAsync(trace_knn + knn_off, gidx, sizeof(int32_t) * (size_t)B * S * K0,
+                                               cudaMemcpyDeviceToDevice, st));
+            }
+            // per-point half of the 1x1 conv: Z = fea . Wfea^T + b   (weight columns [0:Cin] = features)
+            DPM_TRY(linear_launch(src.fea, Cin, Wsa, Cin + 3, bsa, nullptr, 0, Z, Cout, B * src.n, Cout, Cin,
+                                  DPM_ACT_NONE, st));
+            DPM_TRY(group_launch(Z, src.xyz, dst.xyz, gidx, Wsa + Cin, Cin + 3, gsa, besa, (float)r0, dst.fea, B, src.n, S, K0,
+                                 Cout, st));
+        }
+        fps_off += (size_t)B * S;
+        knn_off += (size_t)B * S * K0;
+        // --- InvResMLP blocks (pointnext.py:130-138) ---
+        int32_t *gprev = nullptr;
+        double rprev = -1.0;
+        int kprev = -1;
+        for (int j = 1; j < d->n_blocks[i]; ++j) {
+            const int K = d->nsample[i][j];
+            const double r = d->radius[i][j];
+            const int Ch = Cout * d->expansion;
+            int32_t *g2 = (gprev && r == rprev && K == kprev) ? gprev : a.get<int32_t>((size_t)B * S * K);
+            float *Z2 = a.get<float>((size_t)B * S * Cout);
+            float *la = a.get<float>((size_t)B * S * Cout);
+            float *h1 = a.get<float>((size_t)B * S * Ch);
+            float *h2 = a.get<float>((size_t)B * S * Cout);
+            float *nf = a.get<float>((size_t)B * S * Cout);
+            const float *Wla = W(), *bla = W(), *gla = W(), *bela = W();
+            const float *W1 = W(), *b1 = W(), *g1 = W(), *be1 = W();
+            const float *W2 = W(), *b2 = W(), *g2w = W(), *be2 = W();
+            if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
+            if (!dry) {
+                if (g2 != gprev) {  // identical (r, K) on identical points: one query serves both blocks
+                    const float r2 = (float)(r * r);
+                    DPM_TRY(knn_launch(dst.xyz, dst.xyz, B, S, S, nullptr, dst.len, K, r2, KNN_MODE_HYBRID, nullptr, g2,
+                                       nullptr, st));
+                }
+                if (trace_knn) {
+                    DPM_CHECK_CUDA(cudaMemcpyAsync(trace_knn + knn_off, g2, sizeof(int32_t) * (size_t)B * S * K,
+                                                   cudaMemcpyDeviceToDevice, st));
+                }
+                DPM_TRY(linear_launch(dst.fea, Cout, Wla, Cout + 3, bla, nullptr, 0, Z2, Cout, B * S, Cout, Cout,
+                                      DPM_ACT_NONE, st));
+                DPM_TRY(group_launch(Z2, dst.xyz, dst.xyz, g2, Wla + Cout, Cout + 3, gla, bela, (float)r, la, B, S, S, K, Cout, st));
+                DPM_TRY(linear_launch(la, Cout, W1, Cout, b1, nullptr, 0, h1, Ch, B * S, Ch, Cout, DPM_ACT_NONE, st));
+                DPM_TRY(layernorm_launch(h1, Ch, g1, be1, nullptr, 0, h1, Ch, B * S, Ch, DPM_ACT_RELU, st));
+                DPM_TRY(linear_launch(h1, Ch, W2, Ch, b2, nullptr, 0, h2, Cout, B * S, Cout, Ch, DPM_ACT_NONE, st));
+                DPM_TRY(layernorm_launch(h2, Cout, g2w, be2, dst.fea, Cout, nf, Cout, B * S, Cout, DPM_ACT_RELU, st));
+            }
+            knn_off += (size_t)B * S * K;
+            dst.fea = nf;
+            gprev = g2;
+            rprev = r;
+            kprev = K;
+        }
+        width *= 2;
+    }
+
+    // --- feature propagation (encoder.py:63-67, pointnext.py:188-218) ---
+    int up_in = width;
+    for (int i = 0; i < d->upsample_layers; ++i) {
+        const Level l1 = lv[d->n_stages - i - 1];
+        const Level l2 = lv[nl - 1];
+        const int up_out = d->out_channel > width / 2 ? d->out_channel : width / 2;
+        if (l1.c != width / 2 || l2.c != up_in)
+            return fail(DPM_ERR_SHAPE, "encoder: FPN channel mismatch (%d,%d) vs (%d,%d)", l1.c, l2.c, width / 2, up_in);
+        const int Ccat = l1.c + l2.c;
+        float *cat = a.get<float>((size_t)B * l1.n * Ccat);
+        float *h1 = a.get<float>((size_t)B * l1.n * up_out);
+        float *h2 = a.get<float>((size_t)B * l1.n * up_out);
+        const float *W1 = W(), *b1 = W(), *g1 = W(), *be1 = W();
+        const float *W2 = W(), *b2 = W(), *g2 = W(), *be2 = W();
+        if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
+        if (!dry) {
+            DPM_TRY(fp_interp_launch(l1.xyz, l2.xyz, l1.fea, l2.fea, l2.pad, cat, B, l1.n, l2.n, l1.c, l2.c, st));
+            DPM_TRY(linear_launch(cat, Ccat, W1, Ccat, b1, nullptr, 0, h1, up_out, B * l1.n, up_out, Ccat, DPM_ACT_NONE, st));
+            DPM_TRY(layernorm_launch(h1, up_out, g1, be1, nullptr, 0, h1, up_out, B * l1.n, up_out, DPM_ACT_RELU, st));
+            DPM_TRY(linear_launch(h1, up_out, W2, up_out, b2, nullptr, 0, h2, up_out, B * l1.n, up_out, up_out, DPM_ACT_NONE, st));
+            DPM_TRY(layernorm_launch(h2, up_out, g2, be2, nullptr, 0, h2, up_out, B * l1.n, up_out, DPM_ACT_RELU, st));
+        }
+        Level &nu = lv[nl++];
+        nu = l1;
+        nu.fea = h2;
+        nu.c = up_out;
+        width /= 2;
+        up_in = up_out;
+    }
+
+    const Level fin = lv[nl - 1];
+    if (!dry) {
+        dim3 g((fin.n + 31) / 32, (fin.c + 31) / 32, B);
+        const uint8_t *fpad = fin.pad ? fin.pad : padding;
+        emit_kernel<<<g, 256, 0, st>>>(fin.fea, fin.xyz, fpad, fin.n, fin.c, coor_scale, out_coor, out_fea, out_pad, desc_out);
+        DPM_CHECK_LAUNCH();
+    }
+    return DPM_OK;
+}
+
+}  // namespace dpm
+
+using namespace dpm;
+
+extern "C" int dpm_encoder_num_weights(const dpm_encoder_desc *desc) { return desc ? enc_num_weights(desc) : 0; }
+
+extern "C" int dpm_encoder_out_points(const dpm_encoder_desc *d) {
+    if (!d) return 0;
+    const int lvl = d->n_stages - d->upsample_layers;  // index into [N, npoint...]
+    return lvl <= 0 ? -1 : d->npoint[lvl - 1];
+}
+
+extern "C" size_t dpm_encoder_workspace_bytes(const dpm_encoder_desc *desc, int B, int N) {
+    if (!desc) return 0;
+    Arena a(nullptr, 0);
+    int rc = encoder_run(desc, nullptr, 0, nullptr, 3 > desc->in_channel ? 3 : desc->in_channel, nullptr, B, N, nullptr,
+                         nullptr, nullptr, nullptr, 1.f, nullptr, nullptr, a, nullptr);
+    if (rc != DPM_OK) return 0;
+    return a.off + 256;
+}
+
+extern "C" int dpm_encoder_forward(const dpm_encoder_desc *desc, const float *const *weights, int n_weights,
+                                   const float *points, int C, const uint8_t *padding, int B, int N, float *out_coor,
+                                   float *out_fea, uint8_t *out_pad, float *desc_out, float coor_scale,
+                                   int64_t *trace_fps, int32_t *trace_knn, void *ws, size_t ws_bytes,
+                                   dpm_stream_t stream) {
+    if (!desc || !weights || !points || !ws) return fail(DPM_ERR_ARG, "encoder: null pointer");
+    if (B <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "encoder: bad shape B=%d N=%d", B, N);
+    Arena a(ws, ws_bytes);
+    return encoder_run(desc, weights, n_weights, points, C, padding, B, N, out_coor, out_fea, out_pad, desc_out,
+                       coor_scale, trace_fps, trace_knn, a, (cudaStream_t)stream);
+}

@@ -1,0 +1,137 @@
+"""Tensor-level front-ends of the index ops, with pytorch3d.ops-compatible signatures.
+
+These are what the drop-in `pytorch3d` package (deeppointmap_b200/compat/pytorch3d) exports,
+so the unmodified reference's `-t3d` branches (network/encoder/utils.py:11-14, 91-123, 273-285)
+run on libdpm_b200.so.  CUDA tensors only; no CPU fallback.
+"""
+from collections import namedtuple
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _C
+
+_KNN = namedtuple("KNN", "dists idx knn")
+_BallQuery = namedtuple("BallQuery", "dists idx knn")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _lengths(lengths, B: int, P: int, device):
+    if lengths is None:
+        return None
+    if lengths.shape != (B,):
+        raise ValueError("points and lengths must have same batch dimension.")
+    return lengths.to(device=device, dtype=torch.int64).contiguous()
+
+
+def _ws(device, nbytes):
+    return _C.workspaces.get(device, nbytes, f"ops{_C.stream_ptr()}")
+
+
+def sample_farthest_points(points: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                           K: Union[int, list, torch.Tensor] = 50, random_start_point: bool = False):
+    """pytorch3d.ops.sample_farthest_points: (N,P,D) -> (sampled (N,K,D), idx (N,K) int64, -1 padded)."""
+    _C.require_cuda(points)
+    if random_start_point:
+        raise NotImplementedError("random_start_point=True is not on the DeepPointMap path (utils.py:273)")
+    if not isinstance(K, int):
+        ks = torch.as_tensor(K).flatten().tolist()
+        if len(set(ks)) != 1:
+            raise NotImplementedError("per-cloud K is not supported")
+        K = int(ks[0])
+    p = _f32c(points)
+    B, N, D = p.shape
+    if D < 3:
+        raise ValueError("points must have at least 3 columns")
+    L = _lengths(lengths, B, N, p.device)
+    idx = torch.empty((B, K), dtype=torch.int64, device=p.device)
+    out = torch.empty((B, K, D), dtype=torch.float32, device=p.device)
+    lib = _C.lib()
+    nb = lib.dpm_fps_workspace_bytes(B, N, D, K)
+    ws = _ws(p.device, nb)
+    with torch.cuda.device(p.device):
+        _C.check(lib.dpm_fps_f32(p.data_ptr(), B, N, D, _C.ptr(L), K, idx.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), _C.stream_ptr()), "fps")
+    return out, idx
+
+
+def knn_gather(x: torch.Tensor, idx: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pytorch3d.ops.knn_gather: x (N,M,U), idx (N,L,K) -> (N,L,K,U)."""
+    N, M, U = x.shape
+    _, L, K = idx.shape
+    out = x[:, :, None].expand(-1, -1, K, -1).gather(1, idx[:, :, :, None].expand(-1, -1, -1, U))
+    if lengths is not None:
+        mask = torch.arange(K, device=x.device)[None].expand(N, -1) >= lengths[:, None]
+        out = out.masked_fill(mask[:, None, :, None].expand(-1, L, -1, U), 0.0)
+    return out
+
+
+def knn_points(p1: torch.Tensor, p2: torch.Tensor, lengths1=None, lengths2=None, norm: int = 2, K: int = 1,
+               version: int = -1, return_nn: bool = False, return_sorted: bool = True):
+    """pytorch3d.ops.knn_points: squared L2, ascending by (d2, index); idx int64; zero padded."""
+    _C.require_cuda(p1, p2)
+    if norm != 2:
+        raise NotImplementedError("only the L2 norm is on the DeepPointMap path")
+    a, b = _f32c(p1), _f32c(p2)
+    if a.shape[0] != b.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    B, S, D1 = a.shape
+    _, N, D2 = b.shape
+    L1, L2 = _lengths(lengths1, B, S, a.device), _lengths(lengths2, B, N, a.device)
+    idx = torch.empty((B, S, K), dtype=torch.int64, device=a.device)
+    d2 = torch.empty((B, S, K), dtype=torch.float32, device=a.device)
+    lib = _C.lib()
+    ws = _ws(a.device, lib.dpm_knn_workspace_bytes(B, S, N, K))
+    with torch.cuda.device(a.device):
+        _C.check(lib.dpm_knn_f32(a.data_ptr(), D1, b.data_ptr(), D2, B, S, N, _C.ptr(L1), _C.ptr(L2), K,
+                                 idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr()), "knn")
+    nn = knn_gather(p2, idx, lengths2) if return_nn else None
+    return _KNN(dists=d2, idx=idx, knn=nn)
+
+
+def ball_query(p1: torch.Tensor, p2: torch.Tensor, lengths1=None, lengths2=None, K: int = 500, radius: float = 0.2,
+               return_nn: bool = True):
+    """pytorch3d.ops.ball_query: first K points (index order) with d2 < radius**2; -1 / 0 padded."""
+    _C.require_cuda(p1, p2)
+    a, b = _f32c(p1), _f32c(p2)
+    B, S, D1 = a.shape
+    _, N, D2 = b.shape
+    L1, L2 = _lengths(lengths1, B, S, a.device), _lengths(lengths2, B, N, a.device)
+    idx = torch.empty((B, S, K), dtype=torch.int64, device=a.device)
+    d2 = torch.empty((B, S, K), dtype=torch.float32, device=a.device)
+    lib = _C.lib()
+    ws = _ws(a.device, lib.dpm_knn_workspace_bytes(B, S, N, K))
+    r2 = float(np.float32(float(radius) ** 2))
+    with torch.cuda.device(a.device):
+        _C.check(lib.dpm_ball_query_f32(a.data_ptr(), D1, b.data_ptr(), D2, B, S, N, _C.ptr(L1), _C.ptr(L2), K, r2,
+                                        idx.data_ptr(), d2.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr()),
+                 "ball_query")
+    nn = None
+    if return_nn:
+        nn = knn_gather(p2, idx.clamp(min=0), None)
+        nn = nn.masked_fill((idx < 0)[..., None], 0.0)
+    return _BallQuery(dists=d2, idx=idx, knn=nn)
+
+
+def hybrid_query(radius: float, K: int, points: torch.Tensor, centers: torch.Tensor,
+                 points_padding: torch.Tensor) -> torch.Tensor:
+    """Querier.hybrid_query_t3d (network/encoder/utils.py:112-123) as one fused call -> idx (B,S,K) int64."""
+    _C.require_cuda(points, centers)
+    a, b = _f32c(centers), _f32c(points)
+    B, S, D1 = a.shape
+    _, N, D2 = b.shape
+    L2 = (~points_padding).sum(1).to(torch.int64).contiguous()
+    idx = torch.empty((B, S, K), dtype=torch.int64, device=a.device)
+    lib = _C.lib()
+    ws = _ws(a.device, lib.dpm_knn_workspace_bytes(B, S, N, K))
+    r2 = float(np.float32(float(radius) ** 2))
+    with torch.cuda.device(a.device):
+        _C.check(lib.dpm_knn_radius_f32(a.data_ptr(), D1, b.data_ptr(), D2, B, S, N, L2.data_ptr(), K, r2,
+                                        idx.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr()), "knn_radius")
+    return idx

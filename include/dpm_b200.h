@@ -1,0 +1,222 @@
+/*
+ * dpm_b200.h -- C ABI of libdpm_b200.so: the B200 (sm_100a) implementation of
+ * DeepPointMap's per-frame hot path (point-cloud encoder + registration decoder).
+ *
+ * Conventions (all entry points):
+ *   - plain C: raw DEVICE pointers + sizes, no torch types.  `stream` is a cudaStream_t
+ *     passed as void*; all work is enqueued on it, nothing synchronises internally
+ *     unless the function is documented as "_host" (then buffers are HOST pointers and
+ *     the call returns when the result is in host memory).
+ *   - return 0 on success, a negative DPM_ERR_* otherwise; dpm_last_error() gives the
+ *     thread-local message.  The callee never allocates or frees caller memory: scratch
+ *     comes from the caller's `ws` buffer (size from the matching *_workspace_bytes).
+ *   - tensors are dense row-major fp32 unless stated; indices int64 (reference dtype);
+ *     masks are 1 byte per element (torch.bool).
+ *   - re-entrant from several host threads as long as each call has its own workspace.
+ *
+ * Each declaration cites the reference interface it replaces, relative to
+ * ZhangXiaze/DeepPointMap (/root/reference) -- or pytorch3d 0.7.4 ("[t3d]"), the
+ * un-vendored dependency whose ops the reference calls at those lines.
+ */
+#ifndef DPM_B200_H
+#define DPM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPM_OK 0
+#define DPM_ERR_SHAPE (-1)       /* bad / inconsistent sizes                          */
+#define DPM_ERR_UNSUPPORTED (-2) /* valid request this build does not implement        */
+#define DPM_ERR_WORKSPACE (-3)   /* ws_bytes smaller than *_workspace_bytes()          */
+#define DPM_ERR_CUDA (-4)        /* a CUDA runtime call failed                         */
+#define DPM_ERR_ARG (-5)         /* null pointer / bad flag                            */
+
+#define DPM_MAX_STAGES 8
+#define DPM_MAX_BLOCKS 4 /* radius_list entries per stage (1 SA + up to 3 InvResMLP) */
+
+typedef void *dpm_stream_t; /* cudaStream_t */
+
+int dpm_version(void);
+const char *dpm_last_error(void);
+/* number of kernel launches enqueued by this host thread since the last reset
+ * (bench.py's "gpu_launches") */
+long long dpm_launch_count(void);
+void dpm_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------
+ * index ops -- seam #3 (pytorch3d.ops) and seam #2 (Sampler / Querier)
+ * ---------------------------------------------------------------------------------- */
+
+/* [t3d] sample_farthest_points(points (B,N,D), lengths, K, random_start_point=False)
+ * called from network/encoder/utils.py:278,282 (Sampler.fps_t3d); same result as the
+ * reference's own Sampler.fps, utils.py:209-270.  Start index 0; d2 = (dx*dx+dy*dy)+dz*dz
+ * in fp32 without FMA; argmax = first maximum; idx = -1 once k >= lengths[b].
+ * idx_out (B,K) int64.  sampled_out (B,K,D) optional (masked_gather, utils.py:298-343:
+ * rows with idx -1 are 0).  lengths (B) int64 on device, NULL = all N. */
+int dpm_fps_f32(const float *points, int B, int N, int D, const int64_t *lengths, int K,
+                int64_t *idx_out, float *sampled_out, void *ws, size_t ws_bytes, dpm_stream_t stream);
+size_t dpm_fps_workspace_bytes(int B, int N, int D, int K);
+
+/* [t3d] knn_points(p1 (B,S,D1), p2 (B,N,D2), lengths1, lengths2, K) -> dists (B,S,K)
+ * squared, ascending by (d2, index); idx (B,S,K) int64.  Only xyz (first 3 columns) is
+ * used (utils.py:94,115 pass [..., :3]).  Slots k >= lengths2[b] and rows
+ * s >= lengths1[b] are 0.  K <= 32.  d2_out may be NULL. */
+int dpm_knn_f32(const float *p1, int D1, const float *p2, int D2, int B, int S, int N,
+                const int64_t *lengths1, const int64_t *lengths2, int K, int64_t *idx_out,
+                float *d2_out, void *ws, size_t ws_bytes, dpm_stream_t stream);
+
+/* Querier.hybrid_query_t3d, network/encoder/utils.py:112-123: knn_points then every
+ * slot with d2 > radius2 takes slot 0's index.  radius2 = fp32(radius**2). */
+int dpm_knn_radius_f32(const float *p1, int D1, const float *p2, int D2, int B, int S, int N,
+                       const int64_t *lengths2, int K, float radius2, int64_t *idx_out, void *ws,
+                       size_t ws_bytes, dpm_stream_t stream);
+
+/* [t3d] ball_query(p1, p2, lengths1, lengths2, K, radius) as used at utils.py:100-110:
+ * the first K points (index order) with d2 < radius2; idx -1 / d2 0 padded. */
+int dpm_ball_query_f32(const float *p1, int D1, const float *p2, int D2, int B, int S, int N,
+                       const int64_t *lengths1, const int64_t *lengths2, int K, float radius2,
+                       int64_t *idx_out, float *d2_out, void *ws, size_t ws_bytes,
+                       dpm_stream_t stream);
+size_t dpm_knn_workspace_bytes(int B, int S, int N, int K);
+
+/* ------------------------------------------------------------------------------------
+ * dense building blocks (row-major activations: one point / token per row)
+ * ---------------------------------------------------------------------------------- */
+
+#define DPM_ACT_NONE 0
+#define DPM_ACT_RELU 1
+
+/* Y (M,N) = act( X (M,K) . W (N,K)^T + bias (N) + res (M,N) ), leading dimensions in
+ * elements.  Replaces the 1x1 Conv1d/Conv2d/Linear calls built by build_mlp
+ * (network/encoder/utils.py:358-389) and the decoder's projections.  bias/res may be NULL. */
+int dpm_linear_f32(const float *X, int ldx, const float *W, int ldw, const float *bias,
+                   const float *res, int ldres, float *Y, int ldy, int M, int N, int K, int act,
+                   dpm_stream_t stream);
+
+/* Y (M,C) = act( LayerNorm_C(X) * gamma + beta + post ), eps 1e-5: LayerNorm1d/2d,
+ * network/encoder/utils.py:392-413, and nn.LayerNorm in descriptor_attention.py:21-23.
+ * post (M,C) optional (residual identity of InvResMLP, pointnext.py:136; positional
+ * embedding of the next attention block, descriptor_attention.py:31,39). */
+int dpm_layernorm_f32(const float *X, int ldx, const float *gamma, const float *beta,
+                      const float *post, int ldpost, float *Y, int ldy, int M, int C, int act,
+                      dpm_stream_t stream);
+
+/* Fused gather + [fea, (xyz-centre)/r] + 1x1 conv + LayerNorm + ReLU + max over K:
+ * SetAbstraction.forward pointnext.py:52-61 / LocalAggregation.forward :97-107.
+ * The 1x1 conv is split algebraically: Zfea (B,N,Cout) = fea . Wfea^T + bias is computed
+ * per POINT beforehand (dpm_linear_f32), the geometric part Wxyz (Cout x 3, row stride
+ * ldw) is applied per gathered neighbour here.  xyz4 (B,N,4), ctr4 (B,S,4) are float4
+ * (x,y,z,0); gidx (B,S,K) int32; out (B,S,Cout). */
+int dpm_group_ln_relu_max_f32(const float *Zfea, const float *xyz4, const float *ctr4,
+                              const int32_t *gidx, const float *Wxyz, int ldw, const float *gamma,
+                              const float *beta, float radius, float *out, int B, int N, int S,
+                              int K, int Cout, dpm_stream_t stream);
+
+/* FeaturePropagation.forward pointnext.py:188-211: 3-NN inverse-squared-distance
+ * interpolation of fea2 (B,S,C2) onto xyz1 (B,N,.) and concat -> out (B,N,C1+C2). */
+int dpm_fp_interp_f32(const float *xyz1_4, const float *xyz2_4, const float *fea1, const float *fea2,
+                      const uint8_t *pad2, float *out, int B, int N, int S, int C1, int C2,
+                      dpm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * whole-path entry points -- seam #1 (network.encoder.Encoder / network.decoder.Decoder)
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct dpm_encoder_desc {
+    int n_stages;                           /* len(encoder.npoint)                       */
+    int in_channel, width, expansion;       /* encoder.in_channel / width / expansion    */
+    int out_channel, upsample_layers;       /* encoder.out_channel / upsample_layers     */
+    int npoint[DPM_MAX_STAGES];             /* encoder.npoint                            */
+    int n_blocks[DPM_MAX_STAGES];           /* len(radius_list[i])                       */
+    double radius[DPM_MAX_STAGES][DPM_MAX_BLOCKS]; /* encoder.radius_list (Python doubles) */
+    int nsample[DPM_MAX_STAGES][DPM_MAX_BLOCKS];
+} dpm_encoder_desc;
+
+/* Encoder.forward, network/encoder/encoder.py:51-69 (+ the descriptor glue of
+ * ExtractionThread.process, system/modules/odometry.py:46-49 when desc_out != NULL).
+ *   points (B,C,N) channel-first, C >= 3; padding (B,N) bool or NULL (= all valid)
+ *   weights: device pointers of the encoder state_dict tensors, in state_dict order
+ *            (point_mlp0.weight, point_mlp0.bias, downsampler.0.sa.mlp.0.weight, ...)
+ *   out_coor (B,3,S), out_fea (B,out_channel,S), out_pad (B,S) bool, S = npoint of the
+ *   level the FPN ends on; desc_out (B,out_channel+3,S) = [fea ; coor*coor_scale] or NULL.
+ *   trace_fps / trace_knn: optional device buffers receiving every stage's FPS indices
+ *   (int64, concatenated (B,npoint[i])) and every query's group indices (int32,
+ *   concatenated (B,S,K)) for parity tests; NULL in production. */
+int dpm_encoder_forward(const dpm_encoder_desc *desc, const float *const *weights, int n_weights,
+                        const float *points, int C, const uint8_t *padding, int B, int N,
+                        float *out_coor, float *out_fea, uint8_t *out_pad, float *desc_out,
+                        float coor_scale, int64_t *trace_fps, int32_t *trace_knn, void *ws,
+                        size_t ws_bytes, dpm_stream_t stream);
+size_t dpm_encoder_workspace_bytes(const dpm_encoder_desc *desc, int B, int N);
+int dpm_encoder_num_weights(const dpm_encoder_desc *desc);
+int dpm_encoder_out_points(const dpm_encoder_desc *desc);
+
+typedef struct dpm_decoder_desc {
+    int in_channel, model_channel, attention_layers, heads; /* decoder.* ; heads = 8   */
+    float tau, eps_offset;                                   /* loss.tau / eps_offset   */
+} dpm_decoder_desc;
+
+/* result record of one registration (device or host memory, 64 floats) */
+#define DPM_REG_R 0        /* 9 floats, row-major R                                    */
+#define DPM_REG_T 9        /* 3 floats                                                 */
+#define DPM_REG_RMSE 12    /* inlier rmse                                              */
+#define DPM_REG_NCORR 13   /* K' = correspondences kept by the offset filter (as float) */
+#define DPM_REG_NINLIER 14 /* K'' = inliers after the SVD loop                          */
+#define DPM_REG_ITERS 15
+#define DPM_REG_STRIDE 16
+
+/* Decoder.registration_forward, network/decoder/decoder.py:91-127, for P independent
+ * (src, dst) pairs (the reference asserts P == 1 per call; P > 1 is the batched form).
+ *   src (P,Cd,M), dst (P,Cd,N) channel-first unified descriptors, Cd = in_channel+3,
+ *   xyz rows in metres.  k = num_pairs sampled per pair (decoder.py:170-178, computed by
+ *   the caller).  weights: decoder state_dict tensors in state_dict order.
+ *   result (P,DPM_REG_STRIDE) floats; conf_out (P,2k) = pairing confidence of the kept
+ *   correspondences in reference order with the inlier ones FIRST COMPACTED:
+ *   conf_out[p][0..K''-1] is what the reference returns. */
+int dpm_registration_forward(const dpm_decoder_desc *desc, const float *const *weights,
+                             int n_weights, const float *src, const float *dst, int P, int M,
+                             int N, int k, float *result, float *conf_out, void *ws,
+                             size_t ws_bytes, dpm_stream_t stream);
+size_t dpm_registration_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N, int k);
+
+/* Decoder.loop_detection_forward, decoder.py:129-143 + OverlapHead heads.py:45-69:
+ * src, dst (P,Cd,L) -> prob (P). */
+int dpm_loop_detection_forward(const dpm_decoder_desc *desc, const float *const *weights,
+                               int n_weights, const float *src, const float *dst, int P, int M,
+                               int N, float *prob, void *ws, size_t ws_bytes, dpm_stream_t stream);
+size_t dpm_loop_detection_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N);
+/* number of entries of `weights` for the decoder calls: the 82 state_dict tensors in
+ * state_dict order (projection, descriptor_attention.{l}.{self_attn,cross_attn}.{in_proj_weight,
+ * in_proj_bias,out_proj.weight,out_proj.bias}, .mlp.{0,2}, .norm{1,2,3}, similarity_head,
+ * offset_head.{mlp.0,mlp.2,mlp.4,downsample,head}, loop_head.{mlp.0,mlp.2,projection.0,
+ * projection.2}, coarse_pairing_head) PLUS one trailing entry: dim_t, the
+ * model_channel/3/2*2 positional-embedding frequencies temperature**(2*(i//2)/npf)
+ * (descriptor_attention.py:70-71), computed once by the host. */
+int dpm_decoder_num_weights(const dpm_decoder_desc *desc);
+
+/* decoder pieces exposed for parity tests */
+/* PositionEmbeddingCoordsSine.forward descriptor_attention.py:66-83: xyz (R,3) metres ->
+ * emb (R,C).  dim_t (npf) = temperature**(2*(i//2)/npf), precomputed by the caller. */
+int dpm_posenc_f32(const float *xyz, int ldx, const float *dim_t, int npf, float *emb, int R, int C,
+                   dpm_stream_t stream);
+/* multi-head attention core: out (Lq, H*32) = softmax(q k^T / sqrt(32)) v per head, for
+ * `nprob` (q-range, kv-range) problems over row-major qkv buffers (nn.MultiheadAttention
+ * core, descriptor_attention.py:33-42).  head_dim must be 32. */
+int dpm_attention_f32(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv,
+                      float *out, int ldo, const int *prob /* device, nprob x 4: q0,Lq,k0,Lk */,
+                      int nprob, int max_lq, int heads, dpm_stream_t stream);
+/* weighted Kabsch + 3-sigma loop, decoder.py:227-265, for P problems of Kc <= ldk
+ * correspondences each: src/dst (P,3,ldk), w (P,ldk), count (P) int32 -> result
+ * (P,DPM_REG_STRIDE), inlier mask (P,ldk) bytes (optional), conf_out (P,ldk) = the inlier
+ * weights compacted in order (optional).  ldk <= 4096. */
+int dpm_kabsch_f32(const float *src, const float *dst, const float *w, const int32_t *count, int P,
+                   int ldk, float *result, uint8_t *inlier, float *conf_out, dpm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPM_B200_H */
