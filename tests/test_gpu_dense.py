@@ -1,0 +1,122 @@
+"""GPU parity of the dense building blocks vs plain torch fp32 (tolerance 1e-5 rel: same
+arithmetic, different summation order)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from deeppointmap_b200 import _C
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def _linear(X, W, b=None, res=None, act=0, ldw=None):
+    M, K = X.shape
+    N = W.shape[0]
+    Y = torch.empty(M, N, device=DEV)
+    rc = _C.lib().dpm_linear_f32(X.data_ptr(), X.stride(0), W.data_ptr(), ldw or W.stride(0), _C.ptr(b), _C.ptr(res),
+                                 N, Y.data_ptr(), N, M, N, K, act, _C.stream_ptr())
+    _C.check(rc)
+    return Y
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (16, 2048, 512), (65, 33, 19), (4096, 128, 32), (512, 768, 256),
+                                   (300, 3, 64), (131, 67, 131), (8192, 32, 16)])
+def test_linear(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    X, W = torch.randn(M, K, generator=g).to(DEV), torch.randn(N, K, generator=g).to(DEV)
+    b, r = torch.randn(N, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    ref = (X.double() @ W.double().T + b.double() + r.double())
+    assert rel_err(_linear(X, W, b, r), ref) < TOL
+    assert rel_err(_linear(X, W, b, None, _C.ACT_RELU), F.relu(X.double() @ W.double().T + b.double())) < TOL
+    assert rel_err(_linear(X, W), X.double() @ W.double().T) < TOL
+
+
+def test_linear_strided_weight_columns():
+    """the SA/LA trick: W = first C columns of a (Cout, C+3) matrix (row stride C+3)."""
+    g = torch.Generator().manual_seed(0)
+    Wfull = torch.randn(64, 35, generator=g).to(DEV)
+    X = torch.randn(1000, 32, generator=g).to(DEV)
+    Y = _linear(X, Wfull, None, None, 0, ldw=35)
+    assert rel_err(Y, X.double() @ Wfull[:, :32].double().T) < TOL
+
+
+@pytest.mark.parametrize("M,C", [(1, 32), (1000, 32), (77, 128), (16, 2048), (4096, 256), (5, 48)])
+def test_layernorm(M, C):
+    g = torch.Generator().manual_seed(C)
+    X = (torch.randn(M, C, generator=g) * 3 + 1).to(DEV)
+    w, b, post = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV), torch.randn(M, C, generator=g).to(DEV)
+    ref = F.layer_norm(X.double(), (C,), w.double(), b.double(), 1e-5)
+    Y = torch.empty_like(X)
+    lib = _C.lib()
+    _C.check(lib.dpm_layernorm_f32(X.data_ptr(), C, w.data_ptr(), b.data_ptr(), 0, 0, Y.data_ptr(), C, M, C, 0, _C.stream_ptr()))
+    assert rel_err(Y, ref) < TOL
+    _C.check(lib.dpm_layernorm_f32(X.data_ptr(), C, w.data_ptr(), b.data_ptr(), post.data_ptr(), C, Y.data_ptr(), C, M, C, 1,
+                                   _C.stream_ptr()))
+    assert rel_err(Y, F.relu(ref + post.double())) < TOL
+    X2 = X.clone()  # in place
+    _C.check(lib.dpm_layernorm_f32(X2.data_ptr(), C, w.data_ptr(), b.data_ptr(), 0, 0, X2.data_ptr(), C, M, C, 1, _C.stream_ptr()))
+    assert rel_err(X2, F.relu(ref)) < TOL
+
+
+@pytest.mark.parametrize("B,N,S,K,C,Cout", [(2, 500, 100, 32, 16, 32), (1, 300, 300, 32, 64, 64), (2, 64, 16, 16, 256, 512),
+                                            (1, 1000, 77, 7, 32, 128), (1, 256, 64, 32, 128, 256)])
+def test_group_ln_relu_max(B, N, S, K, C, Cout):
+    """vs the reference formulation: conv over cat([fea, (xyz-ctr)/r]) -> LN -> ReLU -> max over K."""
+    g = torch.Generator().manual_seed(N + S)
+    xyz, fea = torch.randn(B, N, 3, generator=g), torch.randn(B, N, C, generator=g)
+    ctr = torch.randn(B, S, 3, generator=g)
+    gidx = torch.randint(0, N, (B, S, K), generator=g)
+    W, b = torch.randn(Cout, C + 3, generator=g) / (C ** 0.5), torch.randn(Cout, generator=g)
+    gam, bet, r = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g), 0.37
+    bi = torch.arange(B).view(B, 1, 1)
+    grp = torch.cat([fea[bi, gidx], (xyz[bi, gidx] - ctr[:, :, None]) / r], -1).double()
+    ref = F.relu(F.layer_norm(grp @ W.double().T + b.double(), (Cout,), gam.double(), bet.double(), 1e-5)).max(2)[0]
+
+    def f4(t):
+        return torch.cat([t, torch.zeros(*t.shape[:-1], 1)], -1).contiguous().to(DEV)
+
+    Wd, fead = W.to(DEV), fea.to(DEV)
+    Z = torch.empty(B * N, Cout, device=DEV)
+    lib = _C.lib()
+    bd = b.to(DEV)
+    _C.check(lib.dpm_linear_f32(fead.data_ptr(), C, Wd.data_ptr(), C + 3, bd.data_ptr(), 0, 0, Z.data_ptr(), Cout, B * N, Cout, C,
+                                0, _C.stream_ptr()))
+    out = torch.empty(B, S, Cout, device=DEV)
+    x4, c4, gi = f4(xyz), f4(ctr), gidx.to(torch.int32).to(DEV)
+    gd, btd = gam.to(DEV), bet.to(DEV)
+    _C.check(lib.dpm_group_ln_relu_max_f32(Z.data_ptr(), x4.data_ptr(), c4.data_ptr(), gi.data_ptr(), Wd.data_ptr() + 4 * C,
+                                           C + 3, gd.data_ptr(), btd.data_ptr(), r, out.data_ptr(), B, N, S, K, Cout,
+                                           _C.stream_ptr()))
+    assert rel_err(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,N,S,C1,C2", [(2, 64, 16, 256, 512), (1, 256, 64, 128, 256), (1, 50, 1, 8, 16), (1, 40, 2, 8, 16)])
+def test_fp_interp(B, N, S, C1, C2):
+    g = torch.Generator().manual_seed(S)
+    x2 = torch.randn(B, S, 3, generator=g)
+    x1 = torch.cat([x2, torch.randn(B, N - S, 3, generator=g)], 1)  # deeper level is a subset: exact-zero distances
+    f1, f2 = torch.randn(B, N, C1, generator=g), torch.randn(B, S, C2, generator=g)
+    if S == 1:
+        interp = f2.expand(-1, N, -1).double()
+    else:
+        d = (x1[:, :, None].double() - x2[:, None].double()).pow(2).sum(-1)
+        dd, idx = d.topk(min(3, S), dim=-1, largest=False)
+        w = 1.0 / dd.clamp(min=1e-8)
+        w = w / w.sum(-1, keepdim=True)
+        bi = torch.arange(B).view(B, 1, 1)
+        interp = (f2.double()[bi, idx] * w[..., None]).sum(2)
+    ref = torch.cat([f1.double(), interp], -1)
+
+    def f4(t):
+        return torch.cat([t, torch.zeros(*t.shape[:-1], 1)], -1).contiguous().to(DEV)
+
+    out = torch.empty(B, N, C1 + C2, device=DEV)
+    a, b, c, d_ = f4(x1), f4(x2), f1.to(DEV), f2.to(DEV)
+    _C.check(_C.lib().dpm_fp_interp_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), d_.data_ptr(), 0, out.data_ptr(), B, N, S, C1,
+                                        C2, _C.stream_ptr()))
+    assert rel_err(out, ref) < 2e-5

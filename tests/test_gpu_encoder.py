@@ -1,0 +1,123 @@
+"""GPU parity of the whole encoder (one dpm_encoder_forward call) vs the oracle.
+Bar: FPS / group indices bit-exact; descriptors within 1e-4 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import model_ref as M
+from deeppointmap_b200 import Encoder, data
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4  # north_star: descriptors within 1e-4 rel fp32
+
+
+def _small_cfg():
+    return M._ns(dict(
+        encoder=dict(npoint=[256, 64, 16], radius_list=[[0.1, 0.2], [0.2, 0.4, 0.4], [0.8, 1.6]],
+                     nsample_list=[[32, 32], [16, 16, 16], [16, 16]], in_channel=3, out_channel=64, width=16,
+                     expansion=4, upsample_layers=2),
+        decoder=dict(in_channel=64, model_channel=256, attention_layers=1), loss=dict(tau=0.1, eps_offset=2.0),
+        coor_scale=60.0))
+
+
+def _build(cfg, sd):
+    e = Encoder(cfg).eval()
+    e.load_state_dict(sd, strict=True)
+    e = e.to(DEV)
+    e.trace = True
+    return e
+
+
+def _check(enc, sd, cfg, pts, pad, tol=TOL):
+    tr = {}
+    want = M.encoder_forward(sd, cfg, pts, pad, "direct", trace=tr)
+    with torch.no_grad():
+        got = enc(pts.to(DEV), pad.to(DEV))
+    for a, b in zip(enc.last_trace["fps_idx"], tr["fps_idx"]):
+        assert torch.equal(a.cpu(), b), "FPS indices must be bit-exact"
+    for a, b in zip(enc.last_trace["knn_idx"], tr["knn_idx"]):
+        assert torch.equal(a.cpu().long(), b), "group indices must be bit-exact"
+    assert torch.equal(got[0].cpu(), want[0])  # coordinates are copies
+    assert torch.equal(got[2].cpu(), want[2])
+    assert rel_err(got[1], want[1]) < tol
+    return got, want
+
+
+def test_small_config_random_weights_batch():
+    cfg = _small_cfg()
+    sd = M.random_weights(M.encoder_shapes(cfg), seed=1)
+    enc = _build(cfg, sd)
+    pts = torch.stack([data.kitti_shape_cloud(1, 3000), data.uniform_cube_cloud(2, 3000), data.kitti_shape_cloud(3, 3000)])
+    pad = torch.zeros(3, 3000, dtype=torch.bool)
+    _check(enc, sd, cfg, pts, pad)
+
+
+def test_small_config_ragged_padding():
+    cfg = _small_cfg()
+    sd = M.random_weights(M.encoder_shapes(cfg), seed=2)
+    enc = _build(cfg, sd)
+    pts = torch.stack([data.kitti_shape_cloud(4, 2000), data.kitti_shape_cloud(5, 2000)])
+    pad = torch.zeros(2, 2000, dtype=torch.bool)
+    pad[1, 700:] = True  # valid points at the front (utils.py:212)
+    _check(enc, sd, cfg, pts, pad)
+
+
+def test_fewer_points_than_first_stage():
+    """K > length: FPS emits -1 / zero rows / padded centres (utils.py:234-238)."""
+    cfg = _small_cfg()
+    sd = M.random_weights(M.encoder_shapes(cfg), seed=3)
+    enc = _build(cfg, sd)
+    pts = data.kitti_shape_cloud(6, 400)[None]
+    pad = torch.zeros(1, 400, dtype=torch.bool)
+    pad[:, 200:] = True
+    got, want = _check(enc, sd, cfg, pts, pad)
+    assert enc.last_trace["fps_idx"][0][0, 200:].eq(-1).all()
+
+
+def test_full_config_random_weights_extra_input_channels():
+    cfg = M.default_config()
+    sd = M.random_weights(M.encoder_shapes(cfg), seed=4)
+    enc = _build(cfg, sd)
+    c = data.kitti_shape_cloud(7, 9000)
+    pts = torch.cat([c, torch.ones(1, 9000)], 0)[None]  # (1, 4, N): extra channel is ignored (in_channel 3)
+    pad = torch.zeros(1, 9000, dtype=torch.bool)
+    _check(enc, sd, cfg, pts, pad)
+
+
+def test_full_config_real_weights_sample_frame_golden(cfg, checkpoint, golden_sample):
+    """BASELINE config 1: the sample KITTI frame; vs oracle AND vs the reference-generated fixture."""
+    enc = _build(cfg, checkpoint["encoder"])
+    c0 = torch.from_numpy(golden_sample["cloud0"])
+    pad = torch.zeros(1, c0.shape[1], dtype=torch.bool)
+    _check(enc, checkpoint["encoder"], cfg, c0[None], pad)
+    for i in range(5):
+        assert np.array_equal(enc.last_trace["fps_idx"][i][0].cpu().numpy().astype(np.int32), golden_sample[f"fps0_{i}"])
+    with torch.no_grad():
+        desc = enc.descriptors(c0[None].to(DEV), pad.to(DEV), 60.0)[0]
+    assert rel_err(desc, torch.from_numpy(golden_sample["desc0"])) < TOL
+
+
+def test_full_config_real_weights_65536(cfg, checkpoint):
+    """BASELINE config 2: synthetic 65 536-point cloud."""
+    enc = _build(cfg, checkpoint["encoder"])
+    c = data.kitti_shape_cloud(0, 65536)
+    pad = torch.zeros(1, 65536, dtype=torch.bool)
+    _check(enc, checkpoint["encoder"], cfg, c[None], pad)
+
+
+def test_descriptor_glue_and_determinism(cfg):
+    sd = M.random_weights(M.encoder_shapes(cfg), seed=5)
+    enc = _build(cfg, sd)
+    pts = torch.stack([data.kitti_shape_cloud(8, 5000), data.kitti_shape_cloud(9, 5000)]).to(DEV)
+    with torch.no_grad():
+        coor, fea, pad = enc(pts, None if False else torch.zeros(2, 5000, dtype=torch.bool, device=DEV))
+        d1 = enc.descriptors(pts, None, 60.0)
+        d2 = enc.descriptors(pts, None, 60.0)
+    assert torch.equal(d1, d2)
+    assert torch.equal(d1[:, :128], fea) and torch.equal(d1[:, 128:], coor * 60.0)
+    # batch independence: each frame alone gives the same answer
+    with torch.no_grad():
+        solo = enc.descriptors(pts[1:2], None, 60.0)
+    assert torch.equal(solo[0], d1[1])

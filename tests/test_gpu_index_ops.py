@@ -1,0 +1,134 @@
+"""GPU parity: FPS / kNN / kNN+radius / ball query through the C-ABI vs the C oracle.
+Bar: BIT-EXACT indices (and distances)."""
+import pytest
+import torch
+
+from oracle import index_ops as IO
+from deeppointmap_b200 import data, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _cloud(kind, seed, n):
+    c = data.kitti_shape_cloud(seed, n) if kind == "kitti" else data.uniform_cube_cloud(seed, n)
+    return c.T.contiguous()  # (n, 3)
+
+
+@pytest.mark.parametrize("n,k", [(16, 16), (64, 16), (256, 64), (1000, 100), (1024, 256), (4096, 1024),
+                                 (14500, 4096), (20000, 512), (65536, 4096), (100000, 1024), (131072, 64)])
+def test_fps_bit_exact(n, k):
+    pts = torch.stack([_cloud("kitti", n, n), _cloud("cube", n + 1, n)])
+    want = IO.fps(pts, None, k)
+    _, got = ops.sample_farthest_points(pts.to(DEV), K=k)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_fps_lengths_padding_and_gather():
+    n, k = 3000, 700
+    pts = torch.stack([_cloud("kitti", 1, n), _cloud("cube", 2, n), _cloud("kitti", 3, n)])
+    pts = torch.cat([pts, torch.arange(n, dtype=torch.float32).view(1, n, 1).expand(3, n, 1)], dim=2)  # D = 4
+    lengths = torch.tensor([3000, 500, 1])
+    want = IO.fps(pts, lengths, k)
+    out, got = ops.sample_farthest_points(pts.to(DEV), lengths.to(DEV), K=k)
+    assert torch.equal(got.cpu(), want)
+    assert (got[1, 500:] == -1).all() and (got[2, 1:] == -1).all()
+    ref = torch.gather(pts, 1, want.clamp(min=0)[..., None].expand(-1, -1, 4)).clone()
+    ref[want < 0] = 0
+    assert torch.equal(out.cpu(), ref)  # masked_gather: -1 rows are zero
+
+
+def test_fps_duplicates_first_maximum():
+    pts = torch.zeros(1, 600, 3)
+    pts[0, 300:] = 1.0
+    want = IO.fps(pts, None, 5)
+    _, got = ops.sample_farthest_points(pts.to(DEV), K=5)
+    assert got.cpu().tolist() == want.tolist() == [[0, 300, 0, 0, 0]]
+
+
+def test_fps_batch_of_full_frames():
+    pts = torch.stack([_cloud("kitti", s, 65536) for s in range(3)])
+    want = IO.fps(pts, None, 4096)
+    _, got = ops.sample_farthest_points(pts.to(DEV), K=4096)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_fps_rejects_oversize():
+    with pytest.raises(NotImplementedError):
+        ops.sample_farthest_points(torch.zeros(1, 140000, 3, device=DEV), K=4)
+
+
+@pytest.mark.parametrize("s,n,k", [(16, 16, 16), (64, 256, 32), (256, 1024, 32), (1024, 4096, 32), (300, 5000, 11),
+                                   (4096, 14500, 32), (4096, 65536, 32), (777, 2049, 1), (50, 2048, 17)])
+def test_knn_bit_exact(s, n, k):
+    p2 = torch.stack([_cloud("kitti", n, n), _cloud("cube", n + 5, n)])
+    p1 = torch.stack([p2[0, :s] + 0.001, _cloud("cube", 99, s)])
+    wd, wi = IO.knn(p1, p2, None, k)
+    got = ops.knn_points(p1.to(DEV), p2.to(DEV), K=k)
+    assert torch.equal(got.idx.cpu(), wi)
+    assert torch.equal(got.dists.cpu(), wd)  # distances bit-exact too
+
+
+def test_knn_lengths_and_zero_padding():
+    p2 = torch.stack([_cloud("kitti", 1, 500), _cloud("cube", 2, 500)])
+    p1 = p2[:, :40].clone()
+    l2 = torch.tensor([500, 7])
+    wd, wi = IO.knn(p1, p2, l2, 16)
+    got = ops.knn_points(p1.to(DEV), p2.to(DEV), lengths2=l2.to(DEV), K=16)
+    assert torch.equal(got.idx.cpu(), wi) and torch.equal(got.dists.cpu(), wd)
+    assert (got.idx[1, :, 7:] == 0).all() and (got.dists[1, :, 7:] == 0).all()
+
+
+def test_knn_ties_lower_index_first():
+    p2 = torch.zeros(1, 100, 3)
+    p2[0, 50:] = 2.0
+    got = ops.knn_points(torch.zeros(1, 3, 3, device=DEV), p2.to(DEV), K=32)
+    assert got.idx[0, 0].cpu().tolist() == list(range(32))
+
+
+@pytest.mark.parametrize("s,n,k,r", [(4096, 65536, 32, 0.05), (4096, 4096, 32, 0.1), (1024, 4096, 32, 0.1),
+                                     (256, 256, 32, 0.4), (16, 16, 16, 1.6), (64, 64, 32, 0.8), (500, 3000, 16, 0.02)])
+def test_hybrid_bit_exact(s, n, k, r):
+    p2 = torch.stack([_cloud("kitti", n + 3, n), _cloud("cube", n + 4, n)])
+    p1 = p2[:, torch.randperm(n, generator=torch.Generator().manual_seed(0))[:s]].contiguous()
+    pad = torch.zeros(2, n, dtype=torch.bool)
+    want = IO.hybrid(p1, p2, (~pad).sum(1), k, r)
+    got = ops.hybrid_query(r, k, p2.to(DEV), p1.to(DEV), pad.to(DEV))
+    assert torch.equal(got.cpu(), want)
+
+
+def test_hybrid_no_point_in_radius_and_padding():
+    p2 = _cloud("cube", 1, 400)[None]
+    p1 = torch.tensor([[[5.0, 5.0, 5.0], [0.0, 0.0, 0.0]]])  # first centre far from everything
+    pad = torch.zeros(1, 400, dtype=torch.bool)
+    pad[:, 300:] = True
+    want = IO.hybrid(p1, p2, (~pad).sum(1), 8, 0.05)
+    got = ops.hybrid_query(0.05, 8, p2.to(DEV), p1.to(DEV), pad.to(DEV))
+    assert torch.equal(got.cpu(), want)
+    assert len(set(got[0, 0].cpu().tolist())) == 1  # every slot = the nearest point
+    assert got.max() < 300
+
+
+@pytest.mark.parametrize("k,r", [(8, 0.1), (32, 0.3), (64, 0.2)])
+def test_ball_query_bit_exact(k, r):
+    p2 = torch.stack([_cloud("kitti", 1, 3000), _cloud("cube", 2, 3000)])
+    p1 = p2[:, :200].clone()
+    wd, wi = IO.ball_query(p1, p2, torch.tensor([3000, 1000]), k, r)
+    got = ops.ball_query(p1.to(DEV), p2.to(DEV), lengths2=torch.tensor([3000, 1000], device=DEV), K=k, radius=r,
+                         return_nn=True)
+    assert torch.equal(got.idx.cpu(), wi) and torch.equal(got.dists.cpu(), wd)
+    assert got.knn.shape == (2, 200, k, 3)
+
+
+def test_sortedness_and_idempotence_at_full_size():
+    """Size-independent properties at the BASELINE size (65 536 points)."""
+    p2 = _cloud("kitti", 0, 65536)[None].to(DEV)
+    _, idx = ops.sample_farthest_points(p2, K=4096)
+    assert idx.unique().numel() == 4096 and idx[0, 0] == 0  # FPS never repeats a point on distinct inputs
+    ctr = torch.gather(p2, 1, idx[..., None].expand(-1, -1, 3))
+    res = ops.knn_points(ctr, p2, K=32)
+    assert (res.dists[..., 1:] >= res.dists[..., :-1]).all()  # ascending
+    assert torch.equal(res.idx[..., 0], idx)  # each centre's nearest point is itself (d2 = 0)
+    assert (res.dists[..., 0] == 0).all()
+    again = ops.knn_points(ctr, p2, K=32)
+    assert torch.equal(again.idx, res.idx)  # deterministic
