@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py -- encoder+matcher frames/s at 65 536 points per frame (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One STEP = one pass of the hot path over one batch of F synthetic frames on each GPU:
+  Encoder (FPS, kNN+radius grouping, fused group MLP, FPN) -> F unified descriptor sets,
+  then Decoder.registration_forward for the F consecutive pairs (frame i-1 -> frame i; the
+  first frame of a batch pairs with the last frame of the previous one).
+Frames are independent units: rank r works on its own F frames (weak scaling, no data-path
+collective; the poses are all-gathered once per step, 64 B per frame).
+
+The single JSON line printed by rank 0 follows the driver contract; see DESIGN.md section 6.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "encoder+matcher frames/sec @65536 pts"
+UNIT = "frames/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step (reference EXTRACTOR_BATCHSIZE=32)")
+    ap.add_argument("--points", type=int, default=65536)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_weights(cfg):
+    """The shipped checkpoint when its copy travelled (oracle/_ref/, made by build()); else the
+    modules' seeded default initialisation of the same architecture."""
+    ck = os.path.join(ROOT, "oracle", "_ref", "DeepPointMapAAAI.pth")
+    if os.path.exists(ck):
+        sd = torch.load(ck, map_location="cpu")
+        return sd["encoder"], sd["decoder"], "DeepPointMapAAAI.pth"
+    return None, None, "random-init"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                try:
+                    phys = int(visible.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s), "power_w_max": max(self.power) if self.power else None}
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic frames: a short trajectory per batch (SURVEY.md section 8d generator)
+# ---------------------------------------------------------------------------------------------
+def make_batch(seed: int, frames: int, n: int) -> torch.Tensor:
+    from deeppointmap_b200 import data
+    base = data.kitti_shape_cloud(seed, n)
+    out = [base]
+    for i in range(1, frames):
+        moved, _, _ = data.rigid_move(base, yaw_deg=0.5 * i, t_m=(1.0 * i, 0.05 * i, 0.0), jitter_m=0.01,
+                                      seed=seed * 1000 + i)
+        g = torch.Generator().manual_seed(seed * 1000 + i)
+        out.append(moved[:, torch.randperm(n, generator=g)])
+    return torch.stack(out).contiguous()  # (F, 3, n)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_port_step(esd, dsd, cfg, pts, prev_desc):
+    """One bounded step of the CPU path: encode `pts` (f,3,n) and register the f consecutive
+    pairs.  Returns (descriptors of the last frame, poses)."""
+    from oracle import model_ref as M
+    pad = torch.zeros(pts.shape[0], pts.shape[2], dtype=torch.bool)
+    desc = M.descriptors(esd, cfg, pts, pad, "direct")
+    poses = []
+    chain = [prev_desc] + list(desc) if prev_desc is not None else [desc[-1]] + list(desc)
+    for i in range(1, len(chain)):
+        R, T, conf, rmse = M.registration_forward(dsd, cfg, chain[i - 1], chain[i], 0.5)
+        poses.append((R, T, rmse))
+    return desc[-1], poses
+
+
+def cpu_weights(cfg):
+    from oracle import model_ref as M
+    esd, dsd, name = load_weights(cfg)
+    if esd is None:
+        esd = M.random_weights(M.encoder_shapes(cfg), seed=1)
+        dsd = M.random_weights(M.decoder_shapes(cfg), seed=2)
+    return esd, dsd, name
+
+
+def run_cpu_sample(cfg, n, frames, steps, warmup):
+    from oracle import index_ops
+    esd, dsd, wname = cpu_weights(cfg)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    index_ops.set_num_threads(cores)
+    batches = [make_batch(100 + s, frames, n) for s in range(min(2, max(1, steps)))]
+    prev = None
+    for w in range(warmup):
+        prev, _ = cpu_port_step(esd, dsd, cfg, batches[w % len(batches)], prev)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        prev, _ = cpu_port_step(esd, dsd, cfg, batches[s % len(batches)], prev)
+    dt = time.perf_counter() - t0
+    return {"value": frames * steps / dt, "seconds": dt, "cores": cores, "frames_per_step": frames, "weights": wname}
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path, timed on the host
+    cores.  The reference is pure Python + an un-vendored pytorch3d, and cannot travel to the GPU
+    box, so this is the oracle PORT (oracle/model_ref.py + oracle/dpm_oracle.c: same algorithm,
+    C/OpenMP index ops instead of the Python loops, i.e. a FASTER CPU path than the reference's
+    own fallback).  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from deeppointmap_b200.config import dpm_b_config
+    cfg = dpm_b_config()
+    cores = os.cpu_count() or 1
+    frames = args.cpu_frames or max(1, min(8, cores // 4))
+    r = run_cpu_sample(cfg, args.points, frames, args.steps, args.warmup)
+    sample = (f"{frames} frames x {args.points} pts per step (encoder + {frames} registrations), oracle port, "
+              f"{r['cores']} threads; {args.steps} steps in {r['seconds']:.1f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": f"synthetic; weights {r['weights']}",
+        "config": {"workload": f"synthetic KITTI-shape {args.points}-pt frames, DeepPointMap_B encoder fwd + pairwise "
+                               f"registration (descriptor match + SVD pose), CPU bounded sample of {frames} frames/step"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    from deeppointmap_b200 import Encoder, Decoder, _C
+    from deeppointmap_b200.config import dpm_b_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
+
+    cfg = dpm_b_config()
+    F, n, K, W = args.frames, args.points, args.steps, args.warmup
+    esd, dsd, wname = load_weights(cfg)
+    torch.manual_seed(1234)
+    enc, dec = Encoder(cfg).eval(), Decoder(cfg).eval()
+    if esd is not None:
+        enc.load_state_dict(esd, strict=True)
+        dec.load_state_dict(dsd, strict=True)
+    enc, dec = enc.to(dev), dec.to(dev)
+    S = enc._out_points
+    Cd = enc.final_channel + 3
+
+    # input pool larger than L2 so no timed step finds its input cached
+    bytes_per_batch = F * 3 * n * 4
+    nslots = max(2, -(-int(1.25 * L2_BYTES) // bytes_per_batch))
+    nslots = min(nslots, 64)
+    host_pool = [make_batch((rank * 64 + s) * 7 + 1, F, n).pin_memory() for s in range(nslots)]
+    dev_pool = [h.to(dev) for h in host_pool]
+    pool_mb = nslots * bytes_per_batch / 2 ** 20
+
+    descbuf = torch.zeros((F + 1, Cd, S), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * F, _C.REG_STRIDE), dtype=torch.float32, device=dev) if world > 1 else None
+    k_pairs = dec.num_pairs(0.5, S, S)
+
+    def step(pts):
+        """device-resident step: F frames -> F descriptors -> F poses"""
+        enc.descriptors(pts, None, coor_scale=cfg.coor_scale, out=descbuf[1:])
+        result, conf = dec.registration_forward_batch(descbuf[:F], descbuf[1:], 0.5)
+        descbuf[0].copy_(descbuf[F])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, result)
+        return result, conf
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for w in range(W):
+            step(dev_pool[w % nslots])
+        barrier()
+        # ---- timed region: K steps, CUDA events on the launching (current) stream ----------
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        _C.launch_count_reset()
+        with ClockSampler(local) as clk:
+            t_wall = time.perf_counter()
+            for s in range(K):
+                ev[s][0].record()
+                step(dev_pool[(W + s) % nslots])
+                ev[s][1].record()
+            barrier()
+            t_wall = time.perf_counter() - t_wall
+        launches = _C.launch_count()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = ev[0][0].elapsed_time(ev[-1][1])  # first start -> last end, device time
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        value = world * F * K / (total_ms * 1e-3)
+
+        # ---- end-to-end: pinned host frames in, poses out, through the module API ----------
+        e2e = None
+        if not args.no_e2e:
+            stage = torch.empty((F, 3, n), dtype=torch.float32, device=dev)
+            host_out = torch.empty((F, _C.REG_STRIDE), dtype=torch.float32).pin_memory()
+
+            def e2e_step(hp):
+                stage.copy_(hp, non_blocking=True)
+                result, _ = step(stage)
+                host_out.copy_(result, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return host_out
+
+            for w in range(max(3, W // 2)):
+                e2e_step(host_pool[w % nslots])
+            barrier()
+            t0 = time.perf_counter()
+            for s in range(K):
+                e2e_step(host_pool[(W + s) % nslots])
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * F * K / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": bytes_per_batch,
+                   "d2h_bytes_per_step": F * _C.REG_STRIDE * 4, "ms_per_step": 1e3 * float(tt.item()) / K,
+                   "api": "Encoder.descriptors + Decoder.registration_forward_batch (one C-ABI call each), pinned host "
+                          "input, pose records read back every step"}
+
+        # ---- per-kernel profile pass (CUDA events after every launch, same stream) ---------
+        prof_steps = 3
+        agg = {}
+        for s in range(prof_steps):
+            torch.cuda.synchronize()
+            _C.prof_begin()
+            enc.descriptors(dev_pool[s % nslots], None, coor_scale=cfg.coor_scale, out=descbuf[1:])
+            dec.registration_forward_batch(descbuf[:F], descbuf[1:], 0.5)
+            for tag, a, b, ms in _C.prof_end():
+                e = agg.setdefault((tag, a, b), [0.0, 0])
+                e[0] += ms
+                e[1] += 1
+        kern = sorted(((ms / prof_steps, cnt // prof_steps, tag, a, b) for (tag, a, b), (ms, cnt) in agg.items()),
+                      reverse=True)
+        prof_total = sum(k[0] for k in kern)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------
+    peak, peak_src = peaks()
+    top = kern[0]
+    top_ms, top_cnt, top_tag, ta, tb = top
+    per_launch_ms = top_ms / max(1, top_cnt)
+    if top_tag == "fps":
+        alg = 20.0 * ta * (tb - 1) * F  # 20 B per point per iteration (xyz 12 + min-dist r/w 8), SURVEY 8d
+        what = f"fps_kernel N={ta} K={tb} x {F} clouds"
+    elif top_tag == "knn":
+        k0 = cfg.encoder.nsample_list[0][0]
+        alg = (12.0 * ta * tb + 12.0 * ta * k0) * F  # every query streams every candidate xyz, SURVEY 8d
+        what = f"knn_kernel S={ta} N={tb} x {F} clouds"
+    else:
+        alg = None
+        what = f"{top_tag} ({ta},{tb})"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(top_tag)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": what, "achieved": (alg / (per_launch_ms * 1e-3) / 1e9) if alg else None,
+                "peak": peak, "unit": "GB/s", "frac": (alg / (per_launch_ms * 1e-3) / 1e9 / peak) if alg else None,
+                "traffic": traffic, "peak_source": peak_src, "launch_ms": per_launch_ms,
+                "algorithmic_bytes_per_launch": alg, "share_of_step": top_ms / prof_total if prof_total else None}
+    # the second index kernel, for the FPS + ball-query figure of the headline metric
+    index_kernels = {}
+    for ms, cnt, tag, a, b in kern:
+        if tag == "fps" and a == n:
+            index_kernels["fps_stage0"] = {"ms": ms / max(1, cnt), "GBps": 20.0 * a * (b - 1) * F / (ms / max(1, cnt) * 1e-3) / 1e9}
+        if tag == "knn" and b == n:
+            k0 = cfg.encoder.nsample_list[0][0]
+            index_kernels["knn_stage0"] = {"ms": ms / max(1, cnt),
+                                           "GBps": (12.0 * a * b + 12.0 * a * k0) * F / (ms / max(1, cnt) * 1e-3) / 1e9}
+    fps_ms = sum(ms for ms, cnt, tag, a, b in kern if tag == "fps")
+    knn_ms = sum(ms for ms, cnt, tag, a, b in kern if tag == "knn")
+    idx_bytes = 0.0
+    e = cfg.encoder
+    lv = [n] + list(e.npoint)
+    for i, s_ in enumerate(e.npoint):
+        idx_bytes += 20.0 * lv[i] * (s_ - 1)
+        idx_bytes += 12.0 * s_ * lv[i] + 12.0 * s_ * e.nsample_list[i][0]
+        seen = set()
+        for j in range(1, len(e.radius_list[i])):
+            key = (e.radius_list[i][j], e.nsample_list[i][j])
+            if key in seen:
+                continue
+            seen.add(key)
+            idx_bytes += 12.0 * s_ * s_ + 12.0 * s_ * e.nsample_list[i][j]
+    idx_gbps = idx_bytes * F / ((fps_ms + knn_ms) * 1e-3) / 1e9 if fps_ms + knn_ms > 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": f"synthetic; weights {wname}",
+        "config": {"workload": f"synthetic KITTI-shape {n}-pt clouds, DeepPointMap_B encoder fwd + pairwise registration "
+                               f"(descriptor match + SVD pose, 256x256 descriptors, k={k_pairs}); {F} frames per GPU per step",
+                   "frames_per_gpu_per_step": F, "points_per_frame": n, "global_frames_per_step": world * F,
+                   "parallelism": f"frame-parallel x{world}",
+                   "l2": f"inputs rotate over a {pool_mb:.0f} MiB pool of {nslots} batches per GPU (> 126 MB L2)"},
+        "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / K,
+        "clocks": clk.summary(), "roofline": roofline,
+        "index_ops": {"fps_plus_knn_GBps": idx_gbps, "frac_of_peak": idx_gbps / peak if idx_gbps else None,
+                      "algorithmic_bytes_per_frame": idx_bytes, "fps_ms_per_step": fps_ms, "knn_ms_per_step": knn_ms,
+                      **index_kernels},
+        "kernels_ms_per_step": [{"kernel": tag, "a": a, "b": b, "launches": cnt, "ms": round(ms, 4)} for ms, cnt, tag, a, b in kern[:12]],
+        "profiled_step_ms": prof_total, "wall_ms_per_step": 1e3 * t_wall / K,
+        "step_ms_min_med_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
+    }
+
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        frames = args.cpu_frames or max(1, min(8, cores // 4))
+        r = run_cpu_sample(cfg, n, frames, 2, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": f"2 steps x {frames} frames x {n} pts (encoder + {frames} registrations each) after 1 "
+                                          f"warm-up step, oracle port (torch fp32 + C/OpenMP index ops), {r['seconds']:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ _SIGS = {
     "dpm_last_error": ([], ctypes.c_char_p),
     "dpm_launch_count": ([], _ll),
     "dpm_launch_count_reset": ([], None),
+    "dpm_prof_begin": ([_vp], _i),
+    "dpm_prof_end": ([ctypes.c_char_p, _sz], _i),
     "dpm_fps_f32": ([_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_fps_workspace_bytes": ([_i, _i, _i, _i], _sz),
     "dpm_knn_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp], _i),
@@ -137,3 +139,20 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     lib().dpm_launch_count_reset()
+
+
+def prof_begin() -> None:
+    check(lib().dpm_prof_begin(stream_ptr()), "prof_begin")
+
+
+def prof_end():
+    """-> list of (kernel, a, b, ms), one per launch since prof_begin (synchronises)."""
+    buf = ctypes.create_string_buffer(1 << 20)
+    n = lib().dpm_prof_end(buf, len(buf))
+    if n < 0:
+        check(n, "prof_end")
+    out = []
+    for line in buf.value.decode().splitlines():
+        t, a, b, ms = line.split()
+        out.append((t, int(a), int(b), float(ms)))
+    return out

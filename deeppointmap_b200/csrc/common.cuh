@@ -12,7 +12,10 @@ namespace dpm {
 // ---- error plumbing (thread-local, see dpm_last_error) --------------------------------
 char *err_buf();
 int fail(int code, const char *fmt, ...);
-void count_launch(int n = 1);
+// counts the launch; when a profile is open (dpm_prof_begin) also records a CUDA event on `st`
+// so consecutive events bracket each kernel (everything of one call is on one stream).
+void count_launch(const char *tag, cudaStream_t st);
+void prof_note(long long a, long long b);  // detail columns of the NEXT launch record
 
 #define DPM_CHECK_CUDA(expr)                                                                   \
     do {                                                                                       \
@@ -22,9 +25,9 @@ void count_launch(int n = 1);
                              __FILE__, __LINE__);                                              \
     } while (0)
 
-#define DPM_CHECK_LAUNCH()                                                                     \
+#define DPM_CHECK_LAUNCH(tag, st)                                                              \
     do {                                                                                       \
-        dpm::count_launch();                                                                   \
+        dpm::count_launch(tag, st);                                                            \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess)                                                                 \
             return dpm::fail(DPM_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                 \

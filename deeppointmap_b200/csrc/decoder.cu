@@ -62,7 +62,7 @@ int posenc_launch(const float *xyz, int ldx, const float *dim_t, int npf, float 
     if (R <= 0 || C <= 0 || npf <= 0) return fail(DPM_ERR_SHAPE, "posenc: bad shape");
     const long long total = (long long)R * C;
     posenc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xyz, ldx, dim_t, npf, emb, R, C);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("posenc", st);
     return DPM_OK;
 }
 
@@ -206,7 +206,7 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
     }
     dim3 grid((maxLq + 31) / 32, heads, nprob);
     attention_kernel<<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("attention", st);
     return DPM_OK;
 }
 
@@ -682,7 +682,7 @@ int kabsch_launch(const float *src, const float *dst, const float *w, const int3
     if (P <= 0 || ldk <= 0) return fail(DPM_ERR_SHAPE, "kabsch: bad shape");
     if (ldk > KAB_MAX) return fail(DPM_ERR_UNSUPPORTED, "kabsch: %d correspondences exceed the limit %d", ldk, KAB_MAX);
     kabsch_kernel<<<P, KAB_T, 0, st>>>(src, dst, w, count, ldk, result, inlier, conf_out);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("kabsch", st);
     return DPM_OK;
 }
 
@@ -763,7 +763,7 @@ static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float
     const int maxL = M > N ? M : N;
     dim3 g((maxL + 31) / 32, (Cf + 31) / 32, 2 * P);
     dec_unpack_kernel<<<g, 256, 0, st>>>(src, dst, M, N, Cf, fea, xyz);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("dec_unpack", st);
     DPM_TRY(posenc_launch(reinterpret_cast<const float *>(xyz), 4, w.dim_t, npf, pos, R, C, st));
     // x = projection(fea) + pos   (the "+ pos" of the first layer, descriptor_attention.py:31)
     DPM_TRY(linear_launch(fea, Cf, w.proj_w, Cf, w.proj_b, pos, C, x, C, R, C, Cf, DPM_ACT_NONE, st));
@@ -826,17 +826,17 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     DPM_TRY(linear_launch(F, C, w.sim0_w, C, w.sim0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(h, C, w.sim2_w, C, w.sim2_b, nullptr, 0, sim, C, R, C, C, DPM_ACT_NONE, st));
     l2norm_rows_kernel<<<(R + 7) / 8, 256, 0, st>>>(sim, R, C);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("l2norm_rows", st);
     // S_p = A_src . A_dst^T
     DPM_TRY(linear_batched_launch(sim, C, (long long)(M + N) * C, sim + (size_t)M * C, C, (long long)(M + N) * C, nullptr,
                                   nullptr, 0, S, N, (long long)M * N, M, N, C, P, DPM_ACT_NONE, st));
     row_stats_kernel<<<(P * M + 7) / 8, 256, 0, st>>>(S, P * M, N, d->tau, rs);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("row_stats", st);
     col_stats_kernel<<<dim3((N + 31) / 32, P, 1), 256, 0, st>>>(S, M, N, d->tau, cs);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("col_stats", st);
     const long long total = (long long)P * M * N;
     dual_softmax_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, M, N, d->tau, rs, cs, total);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("dual_softmax", st);
     int kp2 = 2;
     while (kp2 < k) kp2 <<= 1;
     const size_t tk_smem = (size_t)kp2 * 8 + 32 * 256 * 4;
@@ -847,10 +847,10 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
         configured = true;
     }
     topk_kernel<<<P, TOPK_T, tk_smem, st>>>(S, M * N, N, k, kp2, si, di, conf);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("topk", st);
     // offset head on [f_s;f_d] and [f_d;f_s]  (heads.py:22-42)
     pair_gather_kernel<<<dim3(K2, P, 1), 256, 0, st>>>(F, C, M, N, k, si, di, X);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("pair_gather", st);
     const int RO = P * K2;
     DPM_TRY(linear_launch(X, 2 * C, w.off0_w, 2 * C, w.off0_b, nullptr, 0, o1, C, RO, C, 2 * C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(o1, C, w.off2_w, C, w.off2_b, nullptr, 0, o2, C / 2, RO, C / 2, C, DPM_ACT_RELU, st));
@@ -858,7 +858,7 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     DPM_TRY(linear_launch(o2, C / 2, w.off4_w, C / 2, w.off4_b, oi, C / 4, o3, C / 4, RO, C / 4, C / 2, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(o3, C / 4, w.offh_w, C / 4, w.offh_b, nullptr, 0, off, 3, RO, 3, C / 4, DPM_ACT_NONE, st));
     corres_kernel<<<P, 256, 0, st>>>(xyz, off, si, di, conf, M, N, k, d->eps_offset * d->eps_offset, csrc, cdst, cw, cnt);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("corres", st);
     DPM_TRY(kabsch_launch(csrc, cdst, cw, cnt, P, K2, result, nullptr, conf_out, st));
     return DPM_OK;
 }
@@ -883,11 +883,11 @@ static int loop_run(const dpm_decoder_desc *d, const float *const *weights, cons
     DPM_TRY(linear_launch(F, C, w.lp0_w, C, w.lp0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(h, C, w.lp2_w, C, w.lp2_b, nullptr, 0, g, C, R, C, C, DPM_ACT_NONE, st));
     token_mean_kernel<<<dim3(P, 2, 1), 256, 0, st>>>(g, C, M, N, mean);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("token_mean", st);
     DPM_TRY(linear_launch(mean, 2 * C, w.lq0_w, 2 * C, w.lq0_b, nullptr, 0, p1, 2 * C, P, 2 * C, 2 * C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(p1, 2 * C, w.lq2_w, 2 * C, w.lq2_b, nullptr, 0, logit, 1, P, 1, 2 * C, DPM_ACT_NONE, st));
     sigmoid_kernel<<<(P + 127) / 128, 128, 0, st>>>(logit, prob, P);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("sigmoid", st);
     return DPM_OK;
 }
 

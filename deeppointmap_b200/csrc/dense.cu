@@ -91,13 +91,14 @@ int linear_batched_launch(const float *X, int ldx, long long sX, const float *W,
                           int N, int K, int nbatch, int act, cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0 || nbatch <= 0) return fail(DPM_ERR_SHAPE, "linear: bad shape M=%d N=%d K=%d", M, N, K);
     dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, nbatch);
+    prof_note((long long)M * nbatch, (long long)N * K);
     const bool vx = (ldx % 4 == 0) && (((uintptr_t)X & 15) == 0) && (sX % 4 == 0);
     const bool vw = (ldw % 4 == 0) && (((uintptr_t)W & 15) == 0) && (sW % 4 == 0);
     if (vx && vw) linear_kernel<true, true><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY);
     else if (vx) linear_kernel<true, false><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY);
     else if (vw) linear_kernel<false, true><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY);
     else linear_kernel<false, false><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("linear", st);
     return DPM_OK;
 }
 
@@ -136,7 +137,7 @@ int layernorm_launch(const float *X, int ldx, const float *gamma, const float *b
                      float *Y, int ldy, int M, int C, int act, cudaStream_t st) {
     if (M <= 0 || C <= 0) return fail(DPM_ERR_SHAPE, "layernorm: bad shape M=%d C=%d", M, C);
     layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(X, ldx, gamma, beta, post, ldpost, Y, ldy, M, C, act);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("layernorm", st);
     return DPM_OK;
 }
 
@@ -209,6 +210,7 @@ int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const i
     if (B <= 0 || N <= 0 || S <= 0) return fail(DPM_ERR_SHAPE, "group: bad shape");
     if (K <= 0 || K > 32) return fail(DPM_ERR_UNSUPPORTED, "group: K=%d not in 1..32", K);
     dim3 grid((S + 7) / 8, B, 1);
+    prof_note(S, Cout);
 #define DPM_GROUP_CASE(cpl)                                                                                     \
     case cpl * 32:                                                                                              \
         group_kernel<cpl><<<grid, 256, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K); \
@@ -219,7 +221,7 @@ int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const i
             return fail(DPM_ERR_UNSUPPORTED, "group: Cout=%d not in {32,64,128,256,512}", Cout);
     }
 #undef DPM_GROUP_CASE
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("group", st);
     return DPM_OK;
 }
 
@@ -288,7 +290,7 @@ int fp_interp_launch(const float4 *xyz1, const float4 *xyz2, const float *fea1, 
     if (B <= 0 || N <= 0 || S <= 0 || C1 < 0 || C2 <= 0) return fail(DPM_ERR_SHAPE, "fp_interp: bad shape");
     dim3 grid((N + 7) / 8, B, 1);
     fp_interp_kernel<<<grid, 256, 0, st>>>(xyz1, xyz2, fea1, fea2, pad2, out, N, S, C1, C2);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("fp_interp", st);
     return DPM_OK;
 }
 

@@ -140,10 +140,10 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
     if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
     if (!dry) {
         pad_to_len_kernel<<<B, 256, 0, st>>>(padding, N, l0.len);
-        DPM_CHECK_LAUNCH();
+        DPM_CHECK_LAUNCH("pad_to_len", st);
         dim3 g((N + 255) / 256, B, 1);
         prep_kernel<<<g, 256, 0, st>>>(points, C, N, d->in_channel, W0, b0, d->width, l0.xyz, l0.fea);
-        DPM_CHECK_LAUNCH();
+        DPM_CHECK_LAUNCH("prep", st);
     }
 
     size_t fps_off = 0, knn_off = 0;
@@ -264,7 +264,7 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
         dim3 g((fin.n + 31) / 32, (fin.c + 31) / 32, B);
         const uint8_t *fpad = fin.pad ? fin.pad : padding;
         emit_kernel<<<g, 256, 0, st>>>(fin.fea, fin.xyz, fpad, fin.n, fin.c, coor_scale, out_coor, out_fea, out_pad, desc_out);
-        DPM_CHECK_LAUNCH();
+        DPM_CHECK_LAUNCH("emit", st);
     }
     return DPM_OK;
 }

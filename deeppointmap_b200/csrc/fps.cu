@@ -191,7 +191,7 @@ static int fps_launch_t(const float4 *xyz4, int B, int N, const int *len32, int 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     DPM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz4, N, len32, K, idx64, idx32, new_xyz4, new_pad, new_len32));
-    count_launch();
+    count_launch("fps", st);
     return DPM_OK;
 }
 
@@ -219,6 +219,7 @@ int fps_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_
         return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the register-resident limit %d", N, 16 * FPS_T * 16);
     int P, CS;
     fps_pick(N, B, &P, &CS);
+    prof_note(N, K);
 #define DPM_FPS_CASE(p, cs)                                                                             \
     if (P == p && CS == cs)                                                                             \
         return fps_launch_t<p, cs>(xyz4, B, N, len32, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
@@ -241,7 +242,7 @@ int pack_xyz4_launch(const float *src, int B, int N, int D, float4 *dst, cudaStr
     long long rows = (long long)B * N;
     if (rows == 0) return DPM_OK;
     pack_xyz4_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(src, rows, D, dst);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("pack_xyz4", st);
     return DPM_OK;
 }
 __global__ void lengths_to_i32_kernel(const int64_t *len64, int B, int N, int *len32) {
@@ -253,7 +254,7 @@ __global__ void lengths_to_i32_kernel(const int64_t *len64, int B, int N, int *l
 }
 int lengths_to_i32_launch(const int64_t *len64, int B, int N, int *len32, cudaStream_t st) {
     lengths_to_i32_kernel<<<(B + 127) / 128, 128, 0, st>>>(len64, B, N, len32);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("lengths_to_i32", st);
     return DPM_OK;
 }
 
@@ -296,7 +297,7 @@ extern "C" int dpm_fps_f32(const float *points, int B, int N, int D, const int64
     if (sampled_out) {
         long long total = (long long)B * K * D;
         gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(points, idx_out, B, N, K, D, sampled_out);
-        DPM_CHECK_LAUNCH();
+        DPM_CHECK_LAUNCH("gather_rows", st);
     }
     return DPM_OK;
 }

@@ -206,7 +206,7 @@ static int knn_launch_t(const float4 *q4, const float4 *p4, int B, int S, int N,
     }
     dim3 grid((S + KNN_WARPS * QW - 1) / (KNN_WARPS * QW), B, 1);
     kern<<<grid, KNN_T, smem, st>>>(q4, p4, S, N, qlen32, plen32, K, cap, mode, idx64, idx32, d2out);
-    DPM_CHECK_LAUNCH();
+    DPM_CHECK_LAUNCH("knn", st);
     return DPM_OK;
 }
 
@@ -221,6 +221,7 @@ int knn_launch(const float4 *q4, const float4 *p4, int B, int S, int N, const in
     }
     const long long sms = device_sm_count();
     const long long warps = (long long)B * ((S + KNN_WARPS - 1) / KNN_WARPS);  // CTAs at QW=1
+    prof_note(S, N);
     if (warps >= 8 * sms)
         return knn_launch_t<4>(q4, p4, B, S, N, qlen32, plen32, K, cap, mode, idx64, idx32, d2out, st);
     if (warps >= 3 * sms)
@@ -301,7 +302,7 @@ static int knn_common(const float *p1, int D1, const float *p2, int D2, int B, i
         dim3 grid((S + 7) / 8, B, 1);
         ball_query_kernel<<<grid, 256, 0, st>>>(q4, p4, S, N, lengths1 ? l1 : nullptr, lengths2 ? l2 : nullptr, K, r2,
                                                 idx_out, d2_out);
-        DPM_CHECK_LAUNCH();
+        DPM_CHECK_LAUNCH("ball_query", st);
         return DPM_OK;
     }
     return knn_launch(q4, p4, B, S, N, lengths1 ? l1 : nullptr, lengths2 ? l2 : nullptr, K, r2,

@@ -183,7 +183,8 @@ class Encoder(nn.Module):
         return s
 
     # ---- forward -----------------------------------------------------------------------------
-    def _run(self, points: Tensor, points_padding: Optional[Tensor], want_desc: bool, coor_scale: float):
+    def _run(self, points: Tensor, points_padding: Optional[Tensor], want_desc: bool, coor_scale: float,
+             desc_out: Optional[Tensor] = None):
         _C.require_cuda(points, points_padding)
         if points.dim() != 3 or points.shape[1] < 3:
             raise ValueError("points must be (B, C>=3, N)")
@@ -202,7 +203,12 @@ class Encoder(nn.Module):
         coor = torch.empty((B, 3, S), dtype=torch.float32, device=dev)
         fea = torch.empty((B, Cout, S), dtype=torch.float32, device=dev)
         opad = torch.empty((B, S), dtype=torch.bool, device=dev)
-        desc = torch.empty((B, Cout + 3, S), dtype=torch.float32, device=dev) if want_desc else None
+        desc = None
+        if want_desc:
+            desc = desc_out if desc_out is not None else torch.empty((B, Cout + 3, S), dtype=torch.float32, device=dev)
+            if (desc.shape != (B, Cout + 3, S) or desc.dtype != torch.float32 or desc.device != dev
+                    or not desc.is_contiguous()):
+                raise ValueError(f"`out` must be a contiguous fp32 ({B}, {Cout + 3}, {S}) tensor on {dev}")
         tf = tk = None
         if self.trace:
             nf = sum(self._desc.npoint[i] for i in range(self._desc.n_stages))
@@ -238,7 +244,8 @@ class Encoder(nn.Module):
         return [coor, fea, pad]
 
     @torch.no_grad()
-    def descriptors(self, points: Tensor, points_padding: Optional[Tensor] = None, coor_scale: float = 60.0) -> Tensor:
+    def descriptors(self, points: Tensor, points_padding: Optional[Tensor] = None, coor_scale: float = 60.0,
+                    out: Optional[Tensor] = None) -> Tensor:
         """Encoder + the glue of ExtractionThread.process (system/modules/odometry.py:46-49):
-        (B, Cout+3, S) = [fea ; coor * coor_scale], written by the same call."""
-        return self._run(points, points_padding, True, coor_scale)[3]
+        (B, Cout+3, S) = [fea ; coor * coor_scale], written by the same call (into `out` if given)."""
+        return self._run(points, points_padding, True, coor_scale, out)[3]

@@ -46,6 +46,14 @@ const char *dpm_last_error(void);
  * (bench.py's "gpu_launches") */
 long long dpm_launch_count(void);
 void dpm_launch_count_reset(void);
+/* per-launch device-time profile of this host thread (bench.py's kernel breakdown and the
+ * roofline.achieved figure).  dpm_prof_begin records a start event on `stream`; while open every
+ * launch of this thread records an event after itself.  dpm_prof_end synchronises on them,
+ * closes the profile and writes one line per launch -- "<kernel> <a> <b> <ms>\n", (a, b) =
+ * kernel-specific sizes, e.g. (N, K) for fps and (S, N) for knn -- into buf; returns the number
+ * of launches (>= 0) or a negative DPM_ERR_*. */
+int dpm_prof_begin(dpm_stream_t stream);
+int dpm_prof_end(char *buf, size_t buf_bytes);
 
 /* ------------------------------------------------------------------------------------
  * index ops -- seam #3 (pytorch3d.ops) and seam #2 (Sampler / Querier)
