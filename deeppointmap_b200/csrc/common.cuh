@@ -86,6 +86,37 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 #endif
 
+// ---- per-cloud uniform cell grid (grid.cu) ------------------------------------------------
+constexpr int GRID_MAXCELL = 32768;   // cells per cloud (the cell size grows until the grid fits)
+constexpr int GRID_MAX_N = 262144;    // 1024 buckets x 32 lanes x 8 points per lane
+constexpr int GRID_MIN_N = 2048;      // below this the brute-force / register kernels win
+struct GridDesc {
+    float ox, oy, oz, inv_h;  // cell of p = floor((p - o) * inv_h), x fastest
+    int gx, gy, gz, ncell;
+    float h;
+    int nvalid;               // points in the grid (= lengths[b])
+    int pad0, pad1;
+};
+struct GridWs {
+    float4 *sorted;   // (B, npad) cell-sorted points, w = original index bits; tail = sentinels
+    int *cell_start;  // (B, GRID_MAXCELL + 1)
+    int *cursor;      // (B, GRID_MAXCELL + 1) scatter cursors
+    int *cellid;      // (B, N)
+    float *mind;      // (B, npad) FPS running min-distances, sorted order
+    GridDesc *desc;   // (B)
+    int npad;
+};
+inline int grid_npad(int N) { return (N + 255) & ~255; }
+inline int grid_ppl(int N) { return N <= 32768 ? 1 : (N <= 65536 ? 2 : (N <= 131072 ? 4 : 8)); }
+size_t grid_ws_bytes(int B, int N);
+bool grid_ws_carve(Arena &a, int B, int N, GridWs *g);
+// hmin: lower bound of the cell size (1.001 x the largest query radius served by this grid; 0 = FPS only)
+int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float hmin, const GridWs &g, cudaStream_t st);
+int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
+                    float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);
+int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
+                    int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st);
+
 // ---- internal launchers shared between translation units ------------------------------
 // xyz4 buffers are float4 (x,y,z,0) rows.
 int fps_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64,

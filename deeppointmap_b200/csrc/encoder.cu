@@ -99,7 +99,19 @@ struct Level {
     uint8_t *pad;
     int *len;
     int n, c;
+    bool has_grid;  // cell grid over this level's points (grid.cu): serves the FPS out of this level, the
+    GridWs grid;    // SA query into it and the LA queries on it
 };
+
+// cell-size floor of the grid on level `lvl` (0 = the input cloud): 1.001 x the largest radius
+// queried on it -- the LA blocks of stage lvl-1 and the SA of stage lvl
+static float level_hmin(const dpm_encoder_desc *d, int lvl) {
+    double r = 0.0;
+    if (lvl < d->n_stages) r = d->radius[lvl][0];
+    if (lvl >= 1)
+        for (int j = 1; j < d->n_blocks[lvl - 1]; ++j) r = d->radius[lvl - 1][j] > r ? d->radius[lvl - 1][j] : r;
+    return (float)(r * 1.001);
+}
 
 static int enc_num_weights(const dpm_encoder_desc *d) {
     int n = 2;
@@ -136,6 +148,8 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
     l0.fea = a.get<float>((size_t)B * N * d->width);
     l0.len = a.get<int>(B);
     l0.pad = nullptr;  // level-0 padding is the caller's tensor
+    l0.has_grid = N >= GRID_MIN_N && N <= GRID_MAX_N;
+    if (l0.has_grid) grid_ws_carve(a, B, N, &l0.grid);
     const float *W0 = W(), *b0 = W();
     if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
     if (!dry) {
@@ -144,6 +158,7 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
         dim3 g((N + 255) / 256, B, 1);
         prep_kernel<<<g, 256, 0, st>>>(points, C, N, d->in_channel, W0, b0, d->width, l0.xyz, l0.fea);
         DPM_CHECK_LAUNCH("prep", st);
+        if (l0.has_grid) DPM_TRY(grid_build_launch(l0.xyz, B, N, l0.len, level_hmin(d, 0), l0.grid, st));
     }
 
     size_t fps_off = 0, knn_off = 0;
@@ -159,6 +174,8 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
         dst.pad = a.get<uint8_t>((size_t)B * S);
         dst.len = a.get<int>(B);
         dst.fea = a.get<float>((size_t)B * S * Cout);
+        dst.has_grid = S >= GRID_MIN_N && S <= GRID_MAX_N && (d->n_blocks[i] > 1 || i + 1 < d->n_stages);
+        if (dst.has_grid) grid_ws_carve(a, B, S, &dst.grid);
         // --- set abstraction (pointnext.py:38-64) ---
         const int K0 = d->nsample[i][0];
         const double r0 = d->radius[i][0];
@@ -167,11 +184,18 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
         const float *Wsa = W(), *bsa = W(), *gsa = W(), *besa = W();
         if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
         if (!dry) {
-            DPM_TRY(fps_launch(src.xyz, B, src.n, src.len, S, trace_fps ? trace_fps + fps_off : nullptr, nullptr, dst.xyz,
-                               dst.pad, dst.len, st));
             const float r2 = (float)(r0 * r0);  // fp32(radius ** 2), utils.py:119
-            DPM_TRY(knn_launch(dst.xyz, src.xyz, B, S, src.n, nullptr, src.len, K0, r2, KNN_MODE_HYBRID, nullptr, gidx,
-                               nullptr, st));
+            if (src.has_grid) {
+                DPM_TRY(fps_grid_launch(src.grid, src.xyz, B, src.n, S, trace_fps ? trace_fps + fps_off : nullptr, nullptr,
+                                        dst.xyz, dst.pad, dst.len, st));
+                DPM_TRY(knn_grid_launch(src.grid, dst.xyz, src.xyz, B, S, src.n, nullptr, K0, r2, nullptr, gidx, st));
+            } else {
+                DPM_TRY(fps_launch(src.xyz, B, src.n, src.len, S, trace_fps ? trace_fps + fps_off : nullptr, nullptr, dst.xyz,
+                                   dst.pad, dst.len, st));
+                DPM_TRY(knn_launch(dst.xyz, src.xyz, B, S, src.n, nullptr, src.len, K0, r2, KNN_MODE_HYBRID, nullptr, gidx,
+                                   nullptr, st));
+            }
+            if (dst.has_grid) DPM_TRY(grid_build_launch(dst.xyz, B, S, dst.len, level_hmin(d, i + 1), dst.grid, st));
             if (trace_knn) {
                 DPM_CHECK_CUDA(cudaMemcpyAsync(trace_knn + knn_off, gidx, sizeof(int32_t) * (size_t)B * S * K0,
                                                cudaMemcpyDeviceToDevice, st));
@@ -205,8 +229,11 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
             if (!dry) {
                 if (g2 != gprev) {  // identical (r, K) on identical points: one query serves both blocks
                     const float r2 = (float)(r * r);
-                    DPM_TRY(knn_launch(dst.xyz, dst.xyz, B, S, S, nullptr, dst.len, K, r2, KNN_MODE_HYBRID, nullptr, g2,
-                                       nullptr, st));
+                    if (dst.has_grid)
+                        DPM_TRY(knn_grid_launch(dst.grid, dst.xyz, dst.xyz, B, S, S, nullptr, K, r2, nullptr, g2, st));
+                    else
+                        DPM_TRY(knn_launch(dst.xyz, dst.xyz, B, S, S, nullptr, dst.len, K, r2, KNN_MODE_HYBRID, nullptr, g2,
+                                           nullptr, st));
                 }
                 if (trace_knn) {
                     DPM_CHECK_CUDA(cudaMemcpyAsync(trace_knn + knn_off, g2, sizeof(int32_t) * (size_t)B * S * K,

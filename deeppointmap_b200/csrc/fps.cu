@@ -278,7 +278,7 @@ extern "C" size_t dpm_fps_workspace_bytes(int B, int N, int D, int K) {
     Arena a(nullptr, 0);
     a.get<float4>((size_t)B * N);
     a.get<int>(B);
-    return a.off + 256;
+    return a.off + grid_ws_bytes(B, N) + 256;
 }
 
 extern "C" int dpm_fps_f32(const float *points, int B, int N, int D, const int64_t *lengths, int K,
@@ -293,7 +293,14 @@ extern "C" int dpm_fps_f32(const float *points, int B, int N, int D, const int64
     int *len32 = a.get<int>(B);
     DPM_TRY(pack_xyz4_launch(points, B, N, D, xyz4, st));
     DPM_TRY(lengths_to_i32_launch(lengths, B, N, len32, st));
-    DPM_TRY(fps_launch(xyz4, B, N, len32, K, idx_out, nullptr, nullptr, nullptr, nullptr, st));
+    if (N >= GRID_MIN_N && N <= GRID_MAX_N) {
+        GridWs g;
+        if (!grid_ws_carve(a, B, N, &g)) return fail(DPM_ERR_WORKSPACE, "fps: workspace too small");
+        DPM_TRY(grid_build_launch(xyz4, B, N, len32, 0.f, g, st));
+        DPM_TRY(fps_grid_launch(g, xyz4, B, N, K, idx_out, nullptr, nullptr, nullptr, nullptr, st));
+    } else {
+        DPM_TRY(fps_launch(xyz4, B, N, len32, K, idx_out, nullptr, nullptr, nullptr, nullptr, st));
+    }
     if (sampled_out) {
         long long total = (long long)B * K * D;
         gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(points, idx_out, B, N, K, D, sampled_out);

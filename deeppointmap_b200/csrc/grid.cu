@@ -1,0 +1,505 @@
+// grid.cu -- a per-cloud uniform cell grid and the two index kernels that use it:
+//
+//   * fps_grid_kernel : EXACT farthest point sampling with bucket pruning.  The cloud is
+//     cell-sorted and cut into buckets of 32*PPL consecutive points; every bucket keeps its
+//     bounding box, its largest min-distance and the point that attains it.  A new sample only
+//     touches the buckets whose box is closer than that largest min-distance -- for all other
+//     buckets min(m_i, d_i) = m_i for every point, so skipping them changes nothing.  The
+//     arithmetic on the touched points is the reference's ((dx*dx+dy*dy)+dz*dz, fp32, no FMA,
+//     first maximum = lowest ORIGINAL index), so the picks are bit-identical to
+//     Sampler.fps (network/encoder/utils.py:209-270) while the work per pick drops from N
+//     points to a few hundred.  One CTA per cloud (the points stay in L2), so a batch of
+//     clouds fills the chip instead of 8 SMs per cloud.
+//   * knn_grid_kernel : the "hybrid" query (kNN capped at the radius,
+//     Querier.hybrid_query_t3d, utils.py:112-123) over the 3x3x3 cell neighbourhood of the
+//     query instead of the whole cloud; same total order (d2, index) => same rows.
+//
+// The within-cell order of the sorted array depends on atomic arrival order; every result is
+// made independent of it by explicit (value, original index) comparisons.
+#include "common.cuh"
+
+namespace dpm {
+
+// ---------------------------------------------------------------------------------------
+// grid build: bbox -> cell size -> count -> scan -> scatter
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int g) {
+    const float t = (p - o) * inv_h;
+    int c = (int)fminf(fmaxf(t, 0.f), (float)(g - 1));
+    return c;
+}
+// unclamped cell coordinate of a query (may lie outside the grid)
+__device__ __forceinline__ int cell_coord_free(float p, float o, float inv_h, int g) {
+    const float t = floorf((p - o) * inv_h);
+    return (int)fminf(fmaxf(t, -2.f), (float)(g + 1));
+}
+
+__global__ void __launch_bounds__(1024)
+grid_bbox_kernel(const float4 *__restrict__ xyz4, int N, const int *__restrict__ len32, float hmin,
+                 GridDesc *__restrict__ desc) {
+    __shared__ float red[6][32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int len = len32 ? min(len32[b], N) : N;
+    const float4 *pts = xyz4 + (size_t)b * N;
+    const float INF = __int_as_float(0x7f800000);
+    float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
+    for (int i = tid; i < len; i += 1024) {
+        const float4 p = pts[i];
+        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int a = 0; a < 3; ++a)
+            for (int w = 1; w < 32; ++w) {
+                red[a][0] = fminf(red[a][0], red[a][w]);
+                red[3 + a][0] = fmaxf(red[3 + a][0], red[3 + a][w]);
+            }
+        GridDesc d;
+        if (len <= 0) {
+            d.ox = d.oy = d.oz = 0.f; d.h = 1.f; d.inv_h = 1.f; d.gx = d.gy = d.gz = 1; d.ncell = 1; d.nvalid = 0;
+        } else {
+            float ex = red[3][0] - red[0][0], ey = red[4][0] - red[1][0], ez = red[5][0] - red[2][0];
+            if (!(ex >= 0.f && ex < 1e30f)) ex = 0.f;  // NaN / inf coordinates: degenerate grid, still correct
+            if (!(ey >= 0.f && ey < 1e30f)) ey = 0.f;
+            if (!(ez >= 0.f && ez < 1e30f)) ez = 0.f;
+            const float emax = fmaxf(ex, fmaxf(ey, ez));
+            const float fl = fmaxf(0.02f * emax, 1e-20f);
+            // ~32 points per occupied cell keeps a bucket within one or two cells
+            float h = cbrtf(fmaxf(ex, fl) * fmaxf(ey, fl) * fmaxf(ez, fl) * 32.f / (float)len);
+            h = fmaxf(h, hmin);
+            if (!(h > 0.f) || !(h < 1e30f)) h = 1.f;
+            int gx, gy, gz;
+            for (int it = 0; it < 200; ++it) {
+                gx = (int)fminf(ex / h, 1e6f) + 1;
+                gy = (int)fminf(ey / h, 1e6f) + 1;
+                gz = (int)fminf(ez / h, 1e6f) + 1;
+                if ((long long)gx * gy * gz <= GRID_MAXCELL) break;
+                h *= 1.26f;
+            }
+            if ((long long)gx * gy * gz > GRID_MAXCELL) { gx = gy = gz = 1; h = fmaxf(emax, 1.f) * 2.f; }
+            d.ox = red[0][0]; d.oy = red[1][0]; d.oz = red[2][0];
+            d.h = h; d.inv_h = 1.0f / h; d.gx = gx; d.gy = gy; d.gz = gz; d.ncell = gx * gy * gz; d.nvalid = len;
+        }
+        d.pad0 = d.pad1 = 0;
+        desc[b] = d;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+grid_count_kernel(const float4 *__restrict__ xyz4, int N, const GridDesc *__restrict__ desc,
+                  int *__restrict__ counts, int *__restrict__ cellid) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const GridDesc d = desc[b];
+    if (i >= d.nvalid) return;
+    const float4 p = xyz4[(size_t)b * N + i];
+    const int cx = cell_coord(p.x, d.ox, d.inv_h, d.gx), cy = cell_coord(p.y, d.oy, d.inv_h, d.gy),
+              cz = cell_coord(p.z, d.oz, d.inv_h, d.gz);
+    const int c = (cz * d.gy + cy) * d.gx + cx;
+    cellid[(size_t)b * N + i] = c;
+    atomicAdd(&counts[(size_t)b * (GRID_MAXCELL + 1) + c], 1);
+}
+
+// exclusive scan of the per-cell counts (in place) + a copy as the scatter cursor
+__global__ void __launch_bounds__(1024)
+grid_scan_kernel(const GridDesc *__restrict__ desc, int *__restrict__ cell_start, int *__restrict__ cursor) {
+    __shared__ int wsum[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncell = desc[b].ncell;
+    int *cs = cell_start + (size_t)b * (GRID_MAXCELL + 1);
+    int *cu = cursor + (size_t)b * (GRID_MAXCELL + 1);
+    const int per = (ncell + 1023) / 1024;
+    const int c0 = tid * per, c1 = min(ncell, c0 + per);
+    int s = 0;
+    for (int c = c0; c < c1; ++c) s += cs[c];
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    int run = wsum[warp] + incl - s;
+    for (int c = c0; c < c1; ++c) {
+        const int n = cs[c];
+        cs[c] = run;
+        cu[c] = run;
+        run += n;
+    }
+    if (tid == 1023) cs[ncell] = run;  // the last thread's running sum is the total (its range may be empty)
+}
+
+__global__ void __launch_bounds__(256)
+grid_scatter_kernel(const float4 *__restrict__ xyz4, int N, int npad, const GridDesc *__restrict__ desc,
+                    const int *__restrict__ cellid, int *__restrict__ cursor, float4 *__restrict__ sorted) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int nvalid = desc[b].nvalid;
+    if (i >= npad) return;
+    float4 *dst = sorted + (size_t)b * npad;
+    if (i < nvalid) {
+        const float4 p = xyz4[(size_t)b * N + i];
+        const int c = cellid[(size_t)b * N + i];
+        const int pos = atomicAdd(&cursor[(size_t)b * (GRID_MAXCELL + 1) + c], 1);
+        dst[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    } else {
+        // tail [nvalid, npad): sentinels that never win (min-distance 0, highest index)
+        dst[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+    }
+}
+
+size_t grid_ws_bytes(int B, int N) {
+    Arena a(nullptr, 0);
+    const int npad = grid_npad(N);
+    a.get<float4>((size_t)B * npad);
+    a.get<int>((size_t)B * (GRID_MAXCELL + 1));
+    a.get<int>((size_t)B * (GRID_MAXCELL + 1));
+    a.get<int>((size_t)B * N);
+    a.get<float>((size_t)B * npad);
+    a.get<GridDesc>((size_t)B);
+    return a.off;
+}
+
+bool grid_ws_carve(Arena &a, int B, int N, GridWs *g) {
+    g->npad = grid_npad(N);
+    g->sorted = a.get<float4>((size_t)B * g->npad);
+    g->cell_start = a.get<int>((size_t)B * (GRID_MAXCELL + 1));
+    g->cursor = a.get<int>((size_t)B * (GRID_MAXCELL + 1));
+    g->cellid = a.get<int>((size_t)B * N);
+    g->mind = a.get<float>((size_t)B * g->npad);
+    g->desc = a.get<GridDesc>((size_t)B);
+    return a.ok();
+}
+
+int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float hmin, const GridWs &g, cudaStream_t st) {
+    if (B <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "grid: bad shape B=%d N=%d", B, N);
+    prof_note(N, 0);
+    grid_bbox_kernel<<<B, 1024, 0, st>>>(xyz4, N, len32, hmin, g.desc);
+    DPM_CHECK_LAUNCH("grid_bbox", st);
+    DPM_CHECK_CUDA(cudaMemsetAsync(g.cell_start, 0, sizeof(int) * (size_t)B * (GRID_MAXCELL + 1), st));
+    dim3 grid((N + 255) / 256, B, 1);
+    grid_count_kernel<<<grid, 256, 0, st>>>(xyz4, N, g.desc, g.cell_start, g.cellid);
+    DPM_CHECK_LAUNCH("grid_count", st);
+    grid_scan_kernel<<<B, 1024, 0, st>>>(g.desc, g.cell_start, g.cursor);
+    DPM_CHECK_LAUNCH("grid_scan", st);
+    dim3 grid2((g.npad + 255) / 256, B, 1);
+    grid_scatter_kernel<<<grid2, 256, 0, st>>>(xyz4, N, g.npad, g.desc, g.cellid, g.cursor, g.sorted);
+    DPM_CHECK_LAUNCH("grid_scatter", st);
+    return DPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// pruned exact FPS: one CTA (32 warps) per cloud; bucket b is owned by lane b/32 of warp b%32
+// so that spatially adjacent buckets are spread over different warps.
+// ---------------------------------------------------------------------------------------
+constexpr int FG_T = 1024;
+
+template <int PPL>
+__global__ void __launch_bounds__(FG_T, 1)
+fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
+                const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
+                int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
+                uint8_t *__restrict__ new_pad, int *__restrict__ new_len32) {
+    constexpr int BS = 32 * PPL;
+    __shared__ unsigned long long skey[2][32];
+    __shared__ float4 sxyz[2][32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int len = desc[b].nvalid;
+    const int kn = min(len, K);
+    const int nb = (len + BS - 1) / BS;  // <= 1024
+    const float4 *P = sorted + (size_t)b * npad;
+    float *M = mind + (size_t)b * npad;
+    const size_t ob = (size_t)b * K;
+    const float INF = __int_as_float(0x7f800000);
+    const int mybucket = lane * 32 + warp;
+    const bool owns = mybucket < nb;
+
+    // ---- prologue: bucket boxes, min-distances = +inf (sentinels 0) -------------------------
+    float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f;  // owner's bucket box
+    unsigned maxbits = 0u, argidx = 0xffffffffu;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int L = 0; L * 32 + warp < nb; ++L) {
+        const int bk = L * 32 + warp;
+        float l0 = INF, l1 = INF, l2 = INF, h0 = -INF, h1 = -INF, h2 = -INF;
+        unsigned mi = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+            const int i = bk * BS + j * 32 + lane;
+            const float4 p = P[i];
+            const unsigned id = __float_as_uint(p.w);
+            const bool valid = id != 0x7fffffffu;
+            M[i] = valid ? INF : 0.f;
+            if (valid) {
+                l0 = fminf(l0, p.x); h0 = fmaxf(h0, p.x);
+                l1 = fminf(l1, p.y); h1 = fmaxf(h1, p.y);
+                l2 = fminf(l2, p.z); h2 = fmaxf(h2, p.z);
+                mi = min(mi, id);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, o)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+            l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o));
+            l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
+        }
+        mi = __reduce_min_sync(0xffffffffu, mi);
+        if (lane == L) {
+            lox = l0; loy = l1; loz = l2; hix = h0; hiy = h1; hiz = h2;
+            maxbits = 0x7f800000u;  // +inf: every bucket is touched by the first sample
+            argidx = mi;
+        }
+    }
+
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (len > 0) {
+        const float4 p0 = xyz4[(size_t)b * N];
+        sx = p0.x; sy = p0.y; sz = p0.z;
+    }
+    if (tid == 0 && kn > 0) {
+        if (idx64) idx64[ob] = 0;
+        if (idx32) idx32[ob] = 0;
+        if (new_xyz4) new_xyz4[ob] = make_float4(sx, sy, sz, 0.f);
+        if (new_pad) new_pad[ob] = 0;
+    }
+    __syncthreads();  // M initialised before any bucket is processed (a bucket is only touched by its own warp,
+                      // but keep the prologue and the loop cleanly separated)
+
+    int par = 0;
+    for (int k = 1; k < kn; ++k) {
+        // ---- which of my warp's buckets can change? ------------------------------------------
+        bool act = false;
+        if (owns) {
+            const float dx = fmaxf(fmaxf(lox - sx, sx - hix), 0.f);
+            const float dy = fmaxf(fmaxf(loy - sy, sy - hiy), 0.f);
+            const float dz = fmaxf(fmaxf(loz - sz, sz - hiz), 0.f);
+            const float lb = (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound of every d2
+            act = lb < __uint_as_float(maxbits);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, act);
+        while (mask) {
+            const int L = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int base = (L * 32 + warp) * BS + lane;
+            float bestv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+            unsigned besti = 0xffffffffu;
+            float4 p[PPL];
+            float m[PPL];
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                p[j] = P[base + j * 32];
+                m[j] = M[base + j * 32];
+            }
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                const float d = d2_exact(sx, sy, sz, p[j].x, p[j].y, p[j].z);
+                const float nm = fminf(m[j], d);
+                if (nm < m[j]) M[base + j * 32] = nm;
+                const unsigned id = __float_as_uint(p[j].w);
+                if (nm > bestv || (nm == bestv && id < besti)) {
+                    bestv = nm; besti = id; bx = p[j].x; by = p[j].y; bz = p[j].z;
+                }
+            }
+            const unsigned bits = __float_as_uint(bestv);  // bestv >= 0: the bit pattern is order preserving
+            const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+            const unsigned wmin = __reduce_min_sync(0xffffffffu, bits == wmax ? besti : 0xffffffffu);
+            const int src = __ffs(__ballot_sync(0xffffffffu, bits == wmax && besti == wmin)) - 1;
+            const float wx = __shfl_sync(0xffffffffu, bx, src);
+            const float wy = __shfl_sync(0xffffffffu, by, src);
+            const float wz = __shfl_sync(0xffffffffu, bz, src);
+            if (lane == L) { maxbits = wmax; argidx = wmin; ax = wx; ay = wy; az = wz; }
+        }
+        // ---- arg-max over all buckets: (value desc, original index asc) -------------------------
+        const unsigned vb = owns ? maxbits : 0u;
+        const unsigned wmax = __reduce_max_sync(0xffffffffu, vb);
+        const unsigned wmin = __reduce_min_sync(0xffffffffu, (owns && vb == wmax) ? argidx : 0xffffffffu);
+        const int src = __ffs(__ballot_sync(0xffffffffu, owns && vb == wmax && argidx == wmin)) - 1;
+        if (lane == max(src, 0)) {
+            skey[par][warp] = src < 0 ? 0ull : (((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - wmin));
+            sxyz[par][warp] = make_float4(ax, ay, az, 0.f);
+        }
+        __syncthreads();
+        const unsigned long long kk = skey[par][lane];
+        const unsigned hi = (unsigned)(kk >> 32), lo = (unsigned)kk;
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const int slot = __ffs(__ballot_sync(0xffffffffu, hi == mh && lo == ml)) - 1;
+        const float4 w = sxyz[par][slot];
+        sx = w.x; sy = w.y; sz = w.z;
+        if (tid == 0) {
+            const unsigned sel = 0xffffffffu - ml;
+            if (idx64) idx64[ob + k] = (int64_t)sel;
+            if (idx32) idx32[ob + k] = (int32_t)sel;
+            if (new_xyz4) new_xyz4[ob + k] = make_float4(sx, sy, sz, 0.f);
+            if (new_pad) new_pad[ob + k] = 0;
+        }
+        par ^= 1;
+    }
+    for (int k = kn + tid; k < K; k += FG_T) {  // K > len: idx -1, zero rows, padded
+        if (idx64) idx64[ob + k] = -1;
+        if (idx32) idx32[ob + k] = -1;
+        if (new_xyz4) new_xyz4[ob + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (new_pad) new_pad[ob + k] = 1;
+    }
+    if (tid == 0 && new_len32) new_len32[b] = kn;
+}
+
+int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
+                    float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
+    if (B <= 0 || N <= 0 || K <= 0) return fail(DPM_ERR_SHAPE, "fps: bad shape B=%d N=%d K=%d", B, N, K);
+    if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
+    const int ppl = grid_ppl(N);
+    prof_note(N, K);
+#define DPM_FG_CASE(p)                                                                                       \
+    case p:                                                                                                  \
+        fps_grid_kernel<p><<<B, FG_T, 0, st>>>(g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, \
+                                               new_pad, new_len32);                                          \
+        break;
+    switch (ppl) {
+        DPM_FG_CASE(1) DPM_FG_CASE(2) DPM_FG_CASE(4) DPM_FG_CASE(8)
+        default:
+            return fail(DPM_ERR_UNSUPPORTED, "fps: no kernel for %d points per lane", ppl);
+    }
+#undef DPM_FG_CASE
+    DPM_CHECK_LAUNCH("fps", st);
+    return DPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// hybrid query over the cell neighbourhood.  Warp per query; the running K-best list is
+// distributed over the lanes (lane l = l-th best), ordered by (d2, original index).
+// ---------------------------------------------------------------------------------------
+constexpr int KG_T = 256;
+
+__global__ void __launch_bounds__(KG_T)
+knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted, int npad,
+                const int *__restrict__ cell_start, const GridDesc *__restrict__ desc,
+                const float4 *__restrict__ p4, int S, int N, const int *__restrict__ qlen32, int K, float cap,
+                int64_t *__restrict__ idx64, int32_t *__restrict__ idx32) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (KG_T / 32) + (threadIdx.x >> 5);
+    if (s >= S) return;  // warp-uniform
+    const GridDesc d = desc[b];
+    const int len = d.nvalid;
+    const int qlen = qlen32 ? min(qlen32[b], S) : S;
+    const size_t o = ((size_t)b * S + s) * K;
+    const unsigned kmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+    const float INF = __int_as_float(0x7f800000);
+    if (s >= qlen) {
+        if (lane < K) {
+            if (idx64) idx64[o + lane] = 0;
+            if (idx32) idx32[o + lane] = 0;
+        }
+        return;
+    }
+    const float4 c = q4[(size_t)b * S + s];
+    const float4 *P = sorted + (size_t)b * npad;
+    const int *cs = cell_start + (size_t)b * (GRID_MAXCELL + 1);
+    const int cx = cell_coord_free(c.x, d.ox, d.inv_h, d.gx), cy = cell_coord_free(c.y, d.oy, d.inv_h, d.gy),
+              cz = cell_coord_free(c.z, d.oz, d.inv_h, d.gz);
+    // lane r < 9 owns the x-row (cy + r%3 - 1, cz + r/3 - 1): one contiguous range of the sorted array
+    int rs = 0, re = 0;
+    if (lane < 9) {
+        const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, d.gx - 1);
+        if (yy >= 0 && yy < d.gy && zz >= 0 && zz < d.gz && x0 <= x1) {
+            const int row = (zz * d.gy + yy) * d.gx;
+            rs = cs[row + x0];
+            re = cs[row + x1 + 1];
+        }
+    }
+    float ld = INF, thrd = cap;  // candidates must satisfy (d, i) < (thrd, thri)
+    int li = 0x7fffffff, thri = -1;
+    for (int r = 0; r < 9; ++r) {
+        const int st = __shfl_sync(0xffffffffu, rs, r), en = __shfl_sync(0xffffffffu, re, r);
+        for (int i0 = st; i0 < en; i0 += 32) {
+            const int i = i0 + lane;
+            float dd = INF;
+            int gi = 0x7fffffff;
+            if (i < en) {
+                const float4 p = P[i];
+                dd = d2_exact(c.x, c.y, c.z, p.x, p.y, p.z);
+                gi = __float_as_int(p.w);
+            }
+            unsigned cm = __ballot_sync(0xffffffffu, dd < thrd || (dd == thrd && gi < thri));
+            while (cm) {
+                const int src = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const float dc = __shfl_sync(0xffffffffu, dd, src);
+                const int ic = __shfl_sync(0xffffffffu, gi, src);
+                if (dc < thrd || (dc == thrd && ic < thri)) {  // warp-uniform re-check against the updated bound
+                    const int pos = __popc(__ballot_sync(0xffffffffu, ld < dc || (ld == dc && li < ic)) & kmask);
+                    const float ud = __shfl_up_sync(0xffffffffu, ld, 1);
+                    const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+                    if (lane > pos) { ld = ud; li = ui; }
+                    if (lane == pos) { ld = dc; li = ic; }
+                    const float kd = __shfl_sync(0xffffffffu, ld, K - 1);
+                    const int ki = __shfl_sync(0xffffffffu, li, K - 1);
+                    if (kd < INF) { thrd = kd; thri = ki; }
+                }
+            }
+        }
+    }
+    const int count = __popc(__ballot_sync(0xffffffffu, ld < INF) & kmask);
+    const int kvalid = min(len, K);
+    int first = __shfl_sync(0xffffffffu, li, 0);
+    if (count == 0 && len > 0) {
+        // nothing inside the radius: slot 0 of the uncapped kNN is the nearest point overall
+        const float4 *pts = p4 + (size_t)b * N;
+        unsigned long long best = ~0ull;
+        for (int i = lane; i < len; i += 32) {
+            const float4 p = pts[i];
+            const float dd = d2_exact(c.x, c.y, c.z, p.x, p.y, p.z);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)i;
+            best = key < best ? key : best;
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, best, sft);
+            best = o2 < best ? o2 : best;
+        }
+        first = (int)(unsigned)best;
+    }
+    const int oi = lane < count ? li : (lane < kvalid ? first : 0);
+    if (lane < K) {
+        if (idx64) idx64[o + lane] = (int64_t)oi;
+        if (idx32) idx32[o + lane] = oi;
+    }
+}
+
+int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
+                    int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
+    if (B <= 0 || S <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "knn: bad shape B=%d S=%d N=%d", B, S, N);
+    if (K <= 0 || K > 32) return fail(DPM_ERR_UNSUPPORTED, "knn: K=%d not in 1..32", K);
+    // keep d2 <= r2  <=>  d2 < nextafter(r2, +inf)
+    const float cap = r2 >= 0.f ? __builtin_nextafterf(r2, __builtin_inff()) : 0.f;
+    prof_note(S, N);
+    dim3 grid((S + KG_T / 32 - 1) / (KG_T / 32), B, 1);
+    knn_grid_kernel<<<grid, KG_T, 0, st>>>(q4, g.sorted, g.npad, g.cell_start, g.desc, p4, S, N, qlen32, K, cap, idx64, idx32);
+    DPM_CHECK_LAUNCH("knn", st);
+    return DPM_OK;
+}
+
+}  // namespace dpm

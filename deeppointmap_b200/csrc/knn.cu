@@ -13,6 +13,8 @@
 // the l-th best), so "is this point closer than the current K-th" is one register compare,
 // and the rare insertion is a ballot + shuffle-up.  For the hybrid query the list is
 // additionally capped at the radius, which removes the warm-up insertions.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace dpm {
@@ -278,7 +280,7 @@ extern "C" size_t dpm_knn_workspace_bytes(int B, int S, int N, int K) {
     a.get<float4>((size_t)B * N);
     a.get<int>(B);
     a.get<int>(B);
-    return a.off + 256;
+    return a.off + grid_ws_bytes(B, N) + 256;
 }
 
 static int knn_common(const float *p1, int D1, const float *p2, int D2, int B, int S, int N,
@@ -304,6 +306,13 @@ static int knn_common(const float *p1, int D1, const float *p2, int D2, int B, i
                                                 idx_out, d2_out);
         DPM_CHECK_LAUNCH("ball_query", st);
         return DPM_OK;
+    }
+    if (which == 1 && N >= GRID_MIN_N && N <= GRID_MAX_N && r2 >= 0.f && K <= 32) {
+        // radius-capped query: only the 3x3x3 cell neighbourhood of a query can hold its answers
+        GridWs g;
+        if (!grid_ws_carve(a, B, N, &g)) return fail(DPM_ERR_WORKSPACE, "knn: workspace too small");
+        DPM_TRY(grid_build_launch(p4, B, N, lengths2 ? l2 : nullptr, 1.001f * sqrtf(r2), g, st));
+        return knn_grid_launch(g, q4, p4, B, S, N, lengths1 ? l1 : nullptr, K, r2, idx_out, nullptr, st);
     }
     return knn_launch(q4, p4, B, S, N, lengths1 ? l1 : nullptr, lengths2 ? l2 : nullptr, K, r2,
                       which == 1 ? KNN_MODE_HYBRID : KNN_MODE_KNN, idx_out, nullptr, d2_out, st);

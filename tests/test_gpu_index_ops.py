@@ -55,7 +55,7 @@ def test_fps_batch_of_full_frames():
 
 def test_fps_rejects_oversize():
     with pytest.raises(NotImplementedError):
-        ops.sample_farthest_points(torch.zeros(1, 140000, 3, device=DEV), K=4)
+        ops.sample_farthest_points(torch.zeros(1, 300000, 3, device=DEV), K=4)
 
 
 @pytest.mark.parametrize("s,n,k", [(16, 16, 16), (64, 256, 32), (256, 1024, 32), (1024, 4096, 32), (300, 5000, 11),
@@ -132,3 +132,63 @@ def test_sortedness_and_idempotence_at_full_size():
     assert (res.dists[..., 0] == 0).all()
     again = ops.knn_points(ctr, p2, K=32)
     assert torch.equal(again.idx, res.idx)  # deterministic
+
+
+# ---- the cell-grid kernels (N >= 2048): ties, padding, degenerate clouds, determinism ----------
+def _lattice(n, seed):
+    """integer-lattice cloud: masses of exactly equal distances (tie-break stress)"""
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randint(0, 12, (n, 3), generator=g).float() * 0.05).contiguous()
+
+
+@pytest.mark.parametrize("n,k", [(2048, 300), (5000, 1000), (40000, 600)])
+def test_fps_grid_ties_on_lattice(n, k):
+    pts = torch.stack([_lattice(n, 1), _lattice(n, 2)])
+    want = IO.fps(pts, None, k)
+    _, got = ops.sample_farthest_points(pts.to(DEV), K=k)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_fps_grid_lengths_and_degenerate_clouds():
+    n, k = 6000, 900
+    pts = torch.stack([_cloud("kitti", 1, n), _cloud("cube", 2, n), torch.zeros(n, 3), _cloud("kitti", 3, n),
+                       _cloud("cube", 4, n) * torch.tensor([1.0, 0.0, 0.0])])  # identical points; a line
+    lengths = torch.tensor([6000, 2500, 6000, 1, 6000])
+    want = IO.fps(pts, lengths, k)
+    _, got = ops.sample_farthest_points(pts.to(DEV), lengths.to(DEV), K=k)
+    assert torch.equal(got.cpu(), want)
+    assert (got[3, 1:] == -1).all()
+
+
+@pytest.mark.parametrize("n,s,k,r", [(2048, 500, 32, 0.11), (8000, 2000, 16, 0.05), (30000, 1000, 32, 0.1)])
+def test_hybrid_grid_ties_on_lattice(n, s, k, r):
+    p2 = torch.stack([_lattice(n, 3), _lattice(n, 4)])
+    p1 = torch.stack([p2[0, :s], _lattice(s, 5) + 0.013])
+    pad = torch.zeros(2, n, dtype=torch.bool)
+    pad[1, n // 2:] = True
+    want = IO.hybrid(p1, p2, (~pad).sum(1), k, r)
+    got = ops.hybrid_query(r, k, p2.to(DEV), p1.to(DEV), pad.to(DEV))
+    assert torch.equal(got.cpu(), want)
+
+
+def test_hybrid_grid_queries_outside_the_cloud_and_huge_radius():
+    n = 4096
+    p2 = _cloud("cube", 7, n)[None]
+    p1 = torch.tensor([[[5.0, 5.0, 5.0], [1.02, 0.0, 0.0], [-1.04, -1.04, -1.04], [0.0, 0.0, 0.0], [1e6, 0.0, 0.0]]])
+    pad = torch.zeros(1, n, dtype=torch.bool)
+    for r in (0.05, 0.3, 50.0):
+        want = IO.hybrid(p1, p2, (~pad).sum(1), 32, r)
+        got = ops.hybrid_query(r, 32, p2.to(DEV), p1.to(DEV), pad.to(DEV))
+        assert torch.equal(got.cpu(), want), r
+
+
+def test_grid_results_are_deterministic():
+    """the cell-sorted layout depends on atomic order; the results must not"""
+    pts = torch.stack([_cloud("kitti", 5, 65536), _lattice(65536, 6)]).to(DEV)
+    ref_f = ops.sample_farthest_points(pts, K=1024)[1]
+    ctr = torch.gather(pts, 1, ref_f[..., None].expand(-1, -1, 3))
+    pad = torch.zeros(2, 65536, dtype=torch.bool, device=DEV)
+    ref_q = ops.hybrid_query(0.05, 32, pts, ctr, pad)
+    for _ in range(3):
+        assert torch.equal(ops.sample_farthest_points(pts, K=1024)[1], ref_f)
+        assert torch.equal(ops.hybrid_query(0.05, 32, pts, ctr, pad), ref_q)
