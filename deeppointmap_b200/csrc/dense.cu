@@ -204,13 +204,109 @@ group_kernel(const float *__restrict__ Z, const float4 *__restrict__ xyz4, const
     for (int i = 0; i < CPL; ++i) o[lane + 32 * i] = best[i];
 }
 
+// ---------------------------------------------------------------------------------------
+// group kernel, lane = neighbour (Cout <= 128): every lane pulls ITS neighbour's whole row into
+// registers (independent 16-byte loads, no per-neighbour shuffles), does the LayerNorm locally,
+// and the max over the K lanes is a butterfly transpose-reduce (C-1 shuffles in total) that
+// leaves C/32 output channels per lane.  Wxyz / gamma / beta are staged in shared memory and
+// read as warp-wide broadcasts.
+// ---------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128)
+group_lane_kernel(const float *__restrict__ Z, const float4 *__restrict__ xyz4, const float4 *__restrict__ ctr4,
+                  const int32_t *__restrict__ gidx, const float *__restrict__ Wxyz, int ldw,
+                  const float *__restrict__ gamma, const float *__restrict__ beta, float radius,
+                  float *__restrict__ out, int N, int S, int K) {
+    __shared__ __align__(16) float sw[5][C];  // wx, wy, wz, gamma, beta
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    for (int c = tid; c < C; c += 128) {
+        sw[0][c] = Wxyz[(size_t)c * ldw];
+        sw[1][c] = Wxyz[(size_t)c * ldw + 1];
+        sw[2][c] = Wxyz[(size_t)c * ldw + 2];
+        sw[3][c] = gamma[c];
+        sw[4][c] = beta[c];
+    }
+    __syncthreads();
+    const int s = blockIdx.x * 4 + (tid >> 5);
+    if (s >= S) return;
+    const float4 c4 = ctr4[(size_t)b * S + s];
+    float v[C];
+    const bool act = lane < K;
+    if (act) {
+        const int j = gidx[((size_t)b * S + s) * K + lane];
+        const float4 p = xyz4[(size_t)b * N + j];
+        const float dx = __fdiv_rn(__fsub_rn(p.x, c4.x), radius);
+        const float dy = __fdiv_rn(__fsub_rn(p.y, c4.y), radius);
+        const float dz = __fdiv_rn(__fsub_rn(p.z, c4.z), radius);
+        const float4 *zr = reinterpret_cast<const float4 *>(Z + ((size_t)b * N + j) * C);
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+            const float4 z = zr[q];
+            const float4 wx = *reinterpret_cast<const float4 *>(&sw[0][4 * q]);
+            const float4 wy = *reinterpret_cast<const float4 *>(&sw[1][4 * q]);
+            const float4 wz = *reinterpret_cast<const float4 *>(&sw[2][4 * q]);
+            v[4 * q + 0] = fmaf(dz, wz.x, fmaf(dy, wy.x, fmaf(dx, wx.x, z.x)));
+            v[4 * q + 1] = fmaf(dz, wz.y, fmaf(dy, wy.y, fmaf(dx, wx.y, z.y)));
+            v[4 * q + 2] = fmaf(dz, wz.z, fmaf(dy, wy.z, fmaf(dx, wx.z, z.z)));
+            v[4 * q + 3] = fmaf(dz, wz.w, fmaf(dy, wy.w, fmaf(dx, wx.w, z.w)));
+            sum += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
+        }
+        const float mean = sum * (1.0f / (float)C);
+        float q2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            v[c] -= mean;
+            q2 = fmaf(v[c], v[c], q2);
+        }
+        const float rstd = 1.0f / sqrtf(q2 * (1.0f / (float)C) + 1e-5f);
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) {
+            const float4 g = *reinterpret_cast<const float4 *>(&sw[3][4 * q]);
+            const float4 be = *reinterpret_cast<const float4 *>(&sw[4][4 * q]);
+            v[4 * q + 0] = fmaxf(fmaf(v[4 * q + 0] * rstd, g.x, be.x), 0.f);
+            v[4 * q + 1] = fmaxf(fmaf(v[4 * q + 1] * rstd, g.y, be.y), 0.f);
+            v[4 * q + 2] = fmaxf(fmaf(v[4 * q + 2] * rstd, g.z, be.z), 0.f);
+            v[4 * q + 3] = fmaxf(fmaf(v[4 * q + 3] * rstd, g.w, be.w), 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = 0.f;  // identity of max over relu(.)
+    }
+    // butterfly: after the step with xor-distance d a lane keeps the half of its channels selected by
+    // its bit d, so lane l ends with channels [l*C/32, (l+1)*C/32)
+    int h = C / 2;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const bool up = (lane & d) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, d));
+        }
+        h >>= 1;
+    }
+    float *o = out + ((size_t)b * S + s) * C + lane * (C / 32);
+#pragma unroll
+    for (int i = 0; i < C / 32; ++i) o[i] = v[i];
+}
+
 int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *Wxyz,
                  int ldw, const float *gamma, const float *beta, float radius, float *out, int B, int N, int S,
                  int K, int Cout, cudaStream_t st) {
     if (B <= 0 || N <= 0 || S <= 0) return fail(DPM_ERR_SHAPE, "group: bad shape");
     if (K <= 0 || K > 32) return fail(DPM_ERR_UNSUPPORTED, "group: K=%d not in 1..32", K);
-    dim3 grid((S + 7) / 8, B, 1);
     prof_note(S, Cout);
+    if ((Cout == 32 || Cout == 64 || Cout == 128) && (((uintptr_t)Z & 15) == 0)) {
+        dim3 g4((S + 3) / 4, B, 1);
+        if (Cout == 32) group_lane_kernel<32><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+        else if (Cout == 64) group_lane_kernel<64><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+        else group_lane_kernel<128><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+        DPM_CHECK_LAUNCH("group", st);
+        return DPM_OK;
+    }
+    dim3 grid((S + 7) / 8, B, 1);
 #define DPM_GROUP_CASE(cpl)                                                                                     \
     case cpl * 32:                                                                                              \
         group_kernel<cpl><<<grid, 256, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K); \
