@@ -765,6 +765,7 @@ static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float
     dec_unpack_kernel<<<g, 256, 0, st>>>(src, dst, M, N, Cf, fea, xyz);
     DPM_CHECK_LAUNCH("dec_unpack", st);
     DPM_TRY(posenc_launch(reinterpret_cast<const float *>(xyz), 4, w.dim_t, npf, pos, R, C, st));
+    set_unit_rows(M < N ? M : N);  // path choice per pair, independent of how many pairs are batched
     // x = projection(fea) + pos   (the "+ pos" of the first layer, descriptor_attention.py:31)
     DPM_TRY(linear_launch(fea, Cf, w.proj_w, Cf, w.proj_b, pos, C, x, C, R, C, Cf, DPM_ACT_NONE, st));
     for (int l = 0; l < d->attention_layers; ++l) {
@@ -823,6 +824,7 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     if (dry) return DPM_OK;
 
     // similarity head + L2 normalise (decoder.py:181-185)
+    set_unit_rows(M < N ? M : N);
     DPM_TRY(linear_launch(F, C, w.sim0_w, C, w.sim0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(h, C, w.sim2_w, C, w.sim2_b, nullptr, 0, sim, C, R, C, C, DPM_ACT_NONE, st));
     l2norm_rows_kernel<<<(R + 7) / 8, 256, 0, st>>>(sim, R, C);
@@ -852,6 +854,7 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     pair_gather_kernel<<<dim3(K2, P, 1), 256, 0, st>>>(F, C, M, N, k, si, di, X);
     DPM_CHECK_LAUNCH("pair_gather", st);
     const int RO = P * K2;
+    set_unit_rows(K2);
     DPM_TRY(linear_launch(X, 2 * C, w.off0_w, 2 * C, w.off0_b, nullptr, 0, o1, C, RO, C, 2 * C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(o1, C, w.off2_w, C, w.off2_b, nullptr, 0, o2, C / 2, RO, C / 2, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(X, 2 * C, w.offd_w, 2 * C, w.offd_b, nullptr, 0, oi, C / 4, RO, C / 4, 2 * C, DPM_ACT_NONE, st));
@@ -880,10 +883,12 @@ static int loop_run(const dpm_decoder_desc *d, const float *const *weights, cons
     float *logit = a.get<float>((size_t)P);
     if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "loop_detection: workspace too small");
     if (dry) return DPM_OK;
+    set_unit_rows(M < N ? M : N);
     DPM_TRY(linear_launch(F, C, w.lp0_w, C, w.lp0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(h, C, w.lp2_w, C, w.lp2_b, nullptr, 0, g, C, R, C, C, DPM_ACT_NONE, st));
     token_mean_kernel<<<dim3(P, 2, 1), 256, 0, st>>>(g, C, M, N, mean);
     DPM_CHECK_LAUNCH("token_mean", st);
+    set_unit_rows(1);
     DPM_TRY(linear_launch(mean, 2 * C, w.lq0_w, 2 * C, w.lq0_b, nullptr, 0, p1, 2 * C, P, 2 * C, 2 * C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(p1, 2 * C, w.lq2_w, 2 * C, w.lq2_b, nullptr, 0, logit, 1, P, 1, 2 * C, DPM_ACT_NONE, st));
     sigmoid_kernel<<<(P + 127) / 128, 128, 0, st>>>(logit, prob, P);

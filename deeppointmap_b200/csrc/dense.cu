@@ -86,10 +86,19 @@ linear_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W,
     }
 }
 
+// Rows of one independent unit (cloud / descriptor pair) in the following linear launches.  The
+// tensor-core path is chosen from THIS, not from the batched row count, so a unit's result is
+// bit-identical whatever else shares the batch.  0 = unknown (use the launch's M).
+static thread_local int g_unit_rows = 0;
+void set_unit_rows(int n) { g_unit_rows = n; }
+
 int linear_batched_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW,
                           const float *bias, const float *res, int ldres, float *Y, int ldy, long long sY, int M,
                           int N, int K, int nbatch, int act, cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0 || nbatch <= 0) return fail(DPM_ERR_SHAPE, "linear: bad shape M=%d N=%d K=%d", M, N, K);
+    const int unit = g_unit_rows > 0 ? (g_unit_rows < M ? g_unit_rows : M) : M;
+    if (unit >= 128 && linear_tc_eligible(X, ldx, sX, W, ldw, sW, M, N, K) && (nbatch == 1 || (sY & 3) == 0))
+        return linear_tc_launch(X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, st);
     dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, nbatch);
     prof_note((long long)M * nbatch, (long long)N * K);
     const bool vx = (ldx % 4 == 0) && (((uintptr_t)X & 15) == 0) && (sX % 4 == 0);
@@ -397,6 +406,7 @@ using namespace dpm;
 extern "C" int dpm_linear_f32(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res,
                               int ldres, float *Y, int ldy, int M, int N, int K, int act, dpm_stream_t stream) {
     if (!X || !W || !Y) return fail(DPM_ERR_ARG, "linear: null pointer");
+    set_unit_rows(0);
     return linear_launch(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, (cudaStream_t)stream);
 }
 

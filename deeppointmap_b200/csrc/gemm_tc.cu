@@ -1,0 +1,315 @@
+// gemm_tc.cu -- Y = act(X W^T + bias + res) on the 5th-generation tensor cores (tcgen05),
+// fp32 in / fp32 out with ERROR-COMPENSATED TF32 ("3xTF32"): every operand is split on the fly
+// into hi = tf32(x) and lo = tf32(x - hi) and the product is accumulated as
+// hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator, which keeps the result within ~1e-6 of
+// the fp32 reference (plain TF32 / BF16 would break the 1e-4 parity bar of the decoder).
+//
+// Replaces the 1x1 Conv1d / Conv2d / Linear layers of build_mlp
+// (network/encoder/utils.py:358-389), nn.MultiheadAttention's in/out projections and the
+// decoder heads (network/decoder/heads.py) for M >= 128 rows.
+//
+// One CTA = one 128 x BN output tile.
+//   warps 0-7 : two producer groups of 4 warps that take alternate 32-wide K blocks (so the global
+//               load latency of one block overlaps the split + store of the other) -- coalesced
+//               16-byte global loads of the X (128 x 32) and W (BN x 32) fp32 tiles, hi/lo split in
+//               registers, st.shared into the canonical K-major SWIZZLE_128B layout the UMMA
+//               descriptors describe; then the epilogue -- tcgen05.ld of the accumulator (one output
+//               row per thread, each group half of the columns), bias / residual / ReLU, 16-byte stores.
+//   warp 8    : allocates TMEM; one elected lane issues 12 tcgen05.mma.kind::tf32 (128 x BN x 8) per
+//               K block and releases the stage with tcgen05.commit -> mbarrier.
+// The split is why the operands are staged by the producer warps instead of by TMA: TMA cannot
+// transform data in flight.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace dpm {
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;            // fp32 elements per K block = one 128-byte swizzle row
+constexpr int THREADS = 288;      // 8 producer/epilogue warps + 1 MMA warp
+constexpr int A_TILE = BM * 128;  // bytes of one 128 x 32 fp32 tile
+
+__device__ __forceinline__ unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
+                                         unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4 in [0,14), leading byte offset (unused for swizzled K-major: 1) in [16,30), stride byte
+// offset = 8 rows x 128 B = 1024 >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in
+// [61,64).  The tile base must be 1024-byte aligned.
+__device__ __forceinline__ unsigned long long smem_desc(unsigned saddr) {
+    return (unsigned long long)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1) at [4,6), A = B = TF32
+// (2) at [7,10) / [10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr unsigned instr_desc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ unsigned swz(int r, int c) {
+    return (unsigned)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4));
+}
+
+template <int ROWS>
+__device__ __forceinline__ void produce_tile(const float *__restrict__ G, int ld, int rows_total, int r0, int K, int k0,
+                                             unsigned char *hi, unsigned char *lo, int tid) {
+    constexpr int ITER = ROWS * 8 / 128;
+    float4 v[ITER];
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int idx = tid + i * 128, r = idx >> 3, c = idx & 7;
+        const int gr = r0 + r, gk = k0 + c * 4;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < rows_total && gk < K) v[i] = __ldg(reinterpret_cast<const float4 *>(G + (size_t)gr * ld + gk));
+    }
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int idx = tid + i * 128, r = idx >> 3, c = idx & 7;
+        float4 h, l;
+        h.x = tf32_rna(v[i].x); l.x = tf32_rna(v[i].x - h.x);
+        h.y = tf32_rna(v[i].y); l.y = tf32_rna(v[i].y - h.y);
+        h.z = tf32_rna(v[i].z); l.z = tf32_rna(v[i].z - h.z);
+        h.w = tf32_rna(v[i].w); l.w = tf32_rna(v[i].w - h.w);
+        const unsigned off = swz(r, c);
+        *reinterpret_cast<float4 *>(hi + off) = h;
+        *reinterpret_cast<float4 *>(lo + off) = l;
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W, int ldw,
+                 const float *__restrict__ bias, const float *__restrict__ res, int ldres, float *__restrict__ Y,
+                 int ldy, int M, int N, int K, int act, long long sX, long long sW, long long sY) {
+    X += (size_t)blockIdx.z * sX;
+    W += (size_t)blockIdx.z * sW;
+    Y += (size_t)blockIdx.z * sY;
+    if (res) res += (size_t)blockIdx.z * sY;
+    constexpr int B_TILE = BN * 128;
+    constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
+    __shared__ unsigned tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nkb = (K + BK - 1) / BK;
+    const unsigned full0 = s32(&bars[0]), empty0 = s32(&bars[STAGES]), accum = s32(&bars[2 * STAGES]);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 128);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // two accumulators: [0, BN) takes hi*hi, [BN, 2BN) the two cross terms.  The tensor core's fp32
+    // accumulation truncates, and that bias grows with the number of additions into a LARGE accumulator;
+    // the cross terms are 2^-11 of the main term, so parking them in their own accumulator cuts the
+    // additions into the main one by 3x (they are summed with IEEE adds in the epilogue).
+    constexpr unsigned TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+    if (warp == 8) tmem_alloc(s32(&tmem_base_s), TCOLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_d = tmem_base_s;
+
+    if (warp < 8) {
+        // ================= producers: group g takes the K blocks kb = g, g + 2, ... =================
+        const int grp = warp >> 2, ptid = tid & 127;
+        for (int kb = grp; kb < nkb; kb += 2) {
+            const int s = kb % STAGES;
+            mbar_wait(empty0 + 8 * s, (unsigned)(((kb / STAGES) & 1) ^ 1));
+            unsigned char *st = smem + (size_t)s * STAGE_BYTES;
+            produce_tile<BM>(X, ldx, M, m0, K, kb * BK, st, st + A_TILE, ptid);
+            produce_tile<BN>(W, ldw, N, n0, K, kb * BK, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ptid);
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(full0 + 8 * s);
+        }
+        // ================= epilogue: one output row per thread =================
+        mbar_wait(accum, 0u);
+        tc_fence_after();
+        const int quarter = warp & 3;  // the TMEM lane quarter this warp may read
+        const int row = m0 + quarter * 32 + lane;
+        constexpr int CHALF = BN >= 64 ? BN / 2 : BN;  // columns per producer group in the epilogue
+        const bool vec = ((ldy & 3) == 0) && ((((uintptr_t)Y) & 15) == 0) && (!bias || ((((uintptr_t)bias) & 15) == 0)) &&
+                         (!res || (((ldres & 3) == 0) && ((((uintptr_t)res) & 15) == 0)));
+#pragma unroll 1
+        for (int cb = grp * CHALF; cb < (BN >= 64 ? (grp + 1) * CHALF : (grp == 0 ? BN : 0)); cb += 32) {
+            if (n0 + cb >= N) break;  // warp-uniform
+            float v[32], vc[32];
+            tmem_ld32(tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)cb, v);
+            tmem_ld32(tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)(BN + cb), vc);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] += vc[c];
+            if (row < M) {
+                float *yr = Y + (size_t)row * ldy + n0 + cb;
+                const float *rr = res ? res + (size_t)row * ldres + n0 + cb : nullptr;
+                if (vec && n0 + cb + 32 <= N) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (bias) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + n0 + cb) + q);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        }
+                        if (rr) {
+                            const float4 r4 = *(reinterpret_cast<const float4 *>(rr) + q);
+                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                        }
+                        if (act == DPM_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *(reinterpret_cast<float4 *>(yr) + q) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (n0 + cb + c < N) {
+                            float o = v[c];
+                            if (bias) o += bias[n0 + cb + c];
+                            if (rr) o += rr[c];
+                            if (act == DPM_ACT_RELU) o = fmaxf(o, 0.f);
+                            yr[c] = o;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ================= MMA issuer: one thread =================
+        constexpr unsigned IDESC = instr_desc(BN < 16 ? 16 : BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(full0 + 8 * s, (unsigned)((kb / STAGES) & 1));
+            tc_fence_after();
+            const unsigned sa = s32(smem + (size_t)s * STAGE_BYTES);
+            const unsigned long long ah = smem_desc(sa), al = smem_desc(sa + A_TILE);
+            const unsigned long long bh = smem_desc(sa + 2 * A_TILE), bl = smem_desc(sa + 2 * A_TILE + B_TILE);
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+                const unsigned long long ko = (unsigned long long)(j * 2);  // 32 bytes >> 4 along K inside the swizzle row
+                mma_tf32(tmem_d, ah + ko, bh + ko, IDESC, (kb | j) != 0 ? 1u : 0u);
+                mma_tf32(tmem_d + BN, ah + ko, bl + ko, IDESC, (kb | j) != 0 ? 1u : 0u);
+                mma_tf32(tmem_d + BN, al + ko, bh + ko, IDESC, 1u);
+            }
+            mma_commit(empty0 + 8 * s);  // stage free once these MMAs have read it
+        }
+        mma_commit(accum);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, TCOLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_t(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
+                    const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
+                    int act, cudaStream_t st) {
+    auto kern = linear_tc_kernel<BN, STAGES>;
+    const size_t smem = (size_t)STAGES * (2 * A_TILE + 2 * BN * 128) + 1024;
+    static thread_local bool configured = false;
+    if (!configured) {
+        DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch);
+    kern<<<grid, THREADS, smem, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY);
+    DPM_CHECK_LAUNCH("linear_tc", st);
+    return DPM_OK;
+}
+
+}  // namespace tc
+
+bool linear_tc_eligible(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, int M, int N, int K) {
+    static const bool off = getenv("DPM_NO_TC") != nullptr;
+    if (off) return false;
+    if (M < 128 || N < 8 || K < 4) return false;
+    if ((K & 3) || (ldx & 3) || (ldw & 3) || (sX & 3) || (sW & 3)) return false;
+    if ((((uintptr_t)X) & 15) || (((uintptr_t)W) & 15)) return false;
+    return true;
+}
+
+int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
+                     const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
+                     int act, cudaStream_t st) {
+    prof_note((long long)M * nbatch, (long long)N * K);
+#define DPM_TC_ARGS X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, st
+    if (N <= 32) return tc::launch_t<32, 4>(DPM_TC_ARGS);
+    if (N <= 64) return tc::launch_t<64, 4>(DPM_TC_ARGS);
+    if (N <= 128) return tc::launch_t<128, 3>(DPM_TC_ARGS);
+    return tc::launch_t<256, 2>(DPM_TC_ARGS);
+#undef DPM_TC_ARGS
+}
+
+}  // namespace dpm

@@ -25,7 +25,8 @@ def _linear(X, W, b=None, res=None, act=0, ldw=None):
 
 
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (16, 2048, 512), (65, 33, 19), (4096, 128, 32), (512, 768, 256),
-                                   (300, 3, 64), (131, 67, 131), (8192, 32, 16)])
+                                   (300, 3, 64), (131, 67, 131), (8192, 32, 16), (16384, 256, 256), (1000, 256, 512),
+                                   (300, 100, 64), (129, 16, 2048), (128, 8, 4), (5000, 768, 36)])
 def test_linear(M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     X, W = torch.randn(M, K, generator=g).to(DEV), torch.randn(N, K, generator=g).to(DEV)
