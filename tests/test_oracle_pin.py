@@ -20,6 +20,10 @@ needs_ref = pytest.mark.skipif(not HAS_REF, reason="/root/reference not present 
 @pytest.fixture(scope="module")
 def reference():
     sys.path[:0] = [os.path.join(ROOT, "deeppointmap_b200", "compat"), REF]
+    # compat/ also holds our pytorch3d.ops package; the pin needs the reference's own pure-torch
+    # fallbacks (CPU), so make `import pytorch3d` fail while its modules are imported and built
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "pytorch3d" or k.startswith("pytorch3d.")}
+    sys.modules["pytorch3d"] = None
     import yaml
     from easydict import EasyDict
     from network.encoder.encoder import Encoder
@@ -30,6 +34,8 @@ def reference():
     enc, dec = Encoder(cfg).eval(), Decoder(cfg).eval()
     enc.load_state_dict(ck["encoder"], strict=True)
     dec.load_state_dict(ck["decoder"], strict=False)
+    del sys.modules["pytorch3d"]
+    sys.modules.update(saved)
     return dict(enc=enc, dec=dec, RU=RU, ck=ck)
 
 
