@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step (reference EXTRACTOR_BATCHSIZE=32)")
     ap.add_argument("--points", type=int, default=65536)
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the steps are issued on round-robin (independent frame sequences, like the "
                          "reference's multi-agent mode): the latency-bound FPS chain of one step overlaps the "
                          "throughput-bound kernels of another")

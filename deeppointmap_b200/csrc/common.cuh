@@ -143,6 +143,12 @@ int layernorm_launch(const float *X, int ldx, const float *gamma, const float *b
 int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *Wxyz,
                  int ldw, const float *gamma, const float *beta, float radius, float *out, int B, int N, int S,
                  int K, int Cout, cudaStream_t st);
+bool group_from_xyz_supported(int Cout);
+// stage-0 SA when the gathered features are the stem conv of the coordinates: no per-point matrix at all
+int group_from_xyz_launch(const float *Wsa, int ldw, const float *bias, const float *W0, const float *b0, int width,
+                          float4 *comp, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *gamma,
+                          const float *beta, float radius, float *out, int B, int N, int S, int K, int Cout,
+                          cudaStream_t st);
 int fp_interp_launch(const float4 *xyz1, const float4 *xyz2, const float *fea1, const float *fea2,
                      const uint8_t *pad2, float *out, int B, int N, int S, int C1, int C2, cudaStream_t st);
 

@@ -46,7 +46,7 @@ linear_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W,
     __shared__ float As[GK][GM + 4];
     __shared__ float Bs[GK][GN + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+    const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;  // M tiles on x: no 65535 limit
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -99,7 +99,7 @@ int linear_batched_launch(const float *X, int ldx, long long sX, const float *W,
     const int unit = g_unit_rows > 0 ? (g_unit_rows < M ? g_unit_rows : M) : M;
     if (unit >= 128 && linear_tc_eligible(X, ldx, sX, W, ldw, sW, M, N, K) && (nbatch == 1 || (sY & 3) == 0))
         return linear_tc_launch(X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, st);
-    dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM, nbatch);
+    dim3 grid((M + GM - 1) / GM, (N + GN - 1) / GN, nbatch);
     prof_note((long long)M * nbatch, (long long)N * K);
     const bool vx = (ldx % 4 == 0) && (((uintptr_t)X & 15) == 0) && (sX % 4 == 0);
     const bool vw = (ldw % 4 == 0) && (((uintptr_t)W & 15) == 0) && (sW % 4 == 0);
@@ -220,13 +220,18 @@ group_kernel(const float *__restrict__ Z, const float4 *__restrict__ xyz4, const
 // leaves C/32 output channels per lane.  Wxyz / gamma / beta are staged in shared memory and
 // read as warp-wide broadcasts.
 // ---------------------------------------------------------------------------------------
-template <int C>
+//
+// FROMXYZ: the gathered features are themselves an affine map of the neighbour's coordinates
+// (stage 0: the stem Conv1d 3->width, encoder.py:53, feeds the SA conv with nothing in between), so
+// Z is not a per-point matrix but the composed table comp[C][4] = (Wfea.W0 | Wfea.b0 + b) made by
+// compose_stem_kernel, and the "gather" is 3 more FMAs per channel on the neighbour's own xyz.
+template <int C, bool FROMXYZ>
 __global__ void __launch_bounds__(128)
 group_lane_kernel(const float *__restrict__ Z, const float4 *__restrict__ xyz4, const float4 *__restrict__ ctr4,
                   const int32_t *__restrict__ gidx, const float *__restrict__ Wxyz, int ldw,
                   const float *__restrict__ gamma, const float *__restrict__ beta, float radius,
                   float *__restrict__ out, int N, int S, int K) {
-    __shared__ __align__(16) float sw[5][C];  // wx, wy, wz, gamma, beta
+    __shared__ __align__(16) float sw[FROMXYZ ? 9 : 5][C];  // wx, wy, wz, gamma, beta [, ax, ay, az, a0]
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     for (int c = tid; c < C; c += 128) {
         sw[0][c] = Wxyz[(size_t)c * ldw];
@@ -234,6 +239,10 @@ group_lane_kernel(const float *__restrict__ Z, const float4 *__restrict__ xyz4, 
         sw[2][c] = Wxyz[(size_t)c * ldw + 2];
         sw[3][c] = gamma[c];
         sw[4][c] = beta[c];
+        if (FROMXYZ) {
+            const float4 a = reinterpret_cast<const float4 *>(Z)[c];
+            sw[5][c] = a.x; sw[6][c] = a.y; sw[7][c] = a.z; sw[8][c] = a.w;
+        }
     }
     __syncthreads();
     const int s = blockIdx.x * 4 + (tid >> 5);
@@ -251,7 +260,19 @@ group_lane_kernel(const float *__restrict__ Z, const float4 *__restrict__ xyz4, 
         float sum = 0.f;
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) {
-            const float4 z = zr[q];
+            float4 z;
+            if (FROMXYZ) {
+                const float4 ax = *reinterpret_cast<const float4 *>(&sw[5][4 * q]);
+                const float4 ay = *reinterpret_cast<const float4 *>(&sw[6][4 * q]);
+                const float4 az = *reinterpret_cast<const float4 *>(&sw[7][4 * q]);
+                const float4 a0 = *reinterpret_cast<const float4 *>(&sw[8][4 * q]);
+                z.x = fmaf(p.z, az.x, fmaf(p.y, ay.x, fmaf(p.x, ax.x, a0.x)));
+                z.y = fmaf(p.z, az.y, fmaf(p.y, ay.y, fmaf(p.x, ax.y, a0.y)));
+                z.z = fmaf(p.z, az.z, fmaf(p.y, ay.z, fmaf(p.x, ax.z, a0.z)));
+                z.w = fmaf(p.z, az.w, fmaf(p.y, ay.w, fmaf(p.x, ax.w, a0.w)));
+            } else {
+                z = zr[q];
+            }
             const float4 wx = *reinterpret_cast<const float4 *>(&sw[0][4 * q]);
             const float4 wy = *reinterpret_cast<const float4 *>(&sw[1][4 * q]);
             const float4 wz = *reinterpret_cast<const float4 *>(&sw[2][4 * q]);
@@ -301,6 +322,46 @@ group_lane_kernel(const float *__restrict__ Z, const float4 *__restrict__ xyz4, 
     for (int i = 0; i < C / 32; ++i) o[i] = v[i];
 }
 
+// comp[c] = (sum_k Wfea[c][k] W0[k][0..2], sum_k Wfea[c][k] b0[k] + b[c]): the stem folded into the
+// per-point half of the stage-0 SA conv (fp64 accumulation, rounded once)
+__global__ void compose_stem_kernel(const float *__restrict__ Wfea, int ldw, const float *__restrict__ bias,
+                                    const float *__restrict__ W0, const float *__restrict__ b0, int width, int Cout,
+                                    float4 *__restrict__ comp) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    double a[4] = {0.0, 0.0, 0.0, bias ? (double)bias[c] : 0.0};
+    for (int k = 0; k < width; ++k) {
+        const double w = Wfea[(size_t)c * ldw + k];
+        a[0] += w * W0[k * 3 + 0];
+        a[1] += w * W0[k * 3 + 1];
+        a[2] += w * W0[k * 3 + 2];
+        if (b0) a[3] += w * b0[k];
+    }
+    comp[c] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+}
+
+bool group_from_xyz_supported(int Cout) { return Cout == 32 || Cout == 64 || Cout == 128; }
+
+int group_from_xyz_launch(const float *Wsa, int ldw, const float *bias, const float *W0, const float *b0, int width,
+                          float4 *comp, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *gamma,
+                          const float *beta, float radius, float *out, int B, int N, int S, int K, int Cout,
+                          cudaStream_t st) {
+    if (B <= 0 || N <= 0 || S <= 0) return fail(DPM_ERR_SHAPE, "group: bad shape");
+    if (K <= 0 || K > 32) return fail(DPM_ERR_UNSUPPORTED, "group: K=%d not in 1..32", K);
+    if (!group_from_xyz_supported(Cout)) return fail(DPM_ERR_UNSUPPORTED, "group_from_xyz: Cout=%d", Cout);
+    compose_stem_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(Wsa, ldw, bias, W0, b0, width, Cout, comp);
+    DPM_CHECK_LAUNCH("compose_stem", st);
+    prof_note(S, Cout);
+    const float *Z = reinterpret_cast<const float *>(comp);
+    const float *Wxyz = Wsa + width;
+    dim3 g4((S + 3) / 4, B, 1);
+    if (Cout == 32) group_lane_kernel<32, true><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+    else if (Cout == 64) group_lane_kernel<64, true><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+    else group_lane_kernel<128, true><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+    DPM_CHECK_LAUNCH("group", st);
+    return DPM_OK;
+}
+
 int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *Wxyz,
                  int ldw, const float *gamma, const float *beta, float radius, float *out, int B, int N, int S,
                  int K, int Cout, cudaStream_t st) {
@@ -309,9 +370,9 @@ int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const i
     prof_note(S, Cout);
     if ((Cout == 32 || Cout == 64 || Cout == 128) && (((uintptr_t)Z & 15) == 0)) {
         dim3 g4((S + 3) / 4, B, 1);
-        if (Cout == 32) group_lane_kernel<32><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
-        else if (Cout == 64) group_lane_kernel<64><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
-        else group_lane_kernel<128><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+        if (Cout == 32) group_lane_kernel<32, false><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+        else if (Cout == 64) group_lane_kernel<64, false><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
+        else group_lane_kernel<128, false><<<g4, 128, 0, st>>>(Z, xyz4, ctr4, gidx, Wxyz, ldw, gamma, beta, radius, out, N, S, K);
         DPM_CHECK_LAUNCH("group", st);
         return DPM_OK;
     }

@@ -23,6 +23,7 @@ prep_kernel(const float *__restrict__ points, int C, int N, int cin, const float
     for (int c = 0; c < 8; ++c) in[c] = c < cin ? p[(size_t)c * N] : 0.f;
     const float x = p[0], y = p[(size_t)N], z = p[(size_t)2 * N];
     xyz4[(size_t)b * N + n] = make_float4(x, y, z, 0.f);
+    if (!F0) return;  // stage 0 folds the stem into its group kernel (group_from_xyz_launch)
     float *f = F0 + ((size_t)b * N + n) * width;
     for (int o = 0; o < width; ++o) {
         float acc = b0 ? b0[o] : 0.f;
@@ -145,7 +146,11 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
     l0.n = N;
     l0.c = d->width;
     l0.xyz = a.get<float4>((size_t)B * N);
-    l0.fea = a.get<float>((size_t)B * N * d->width);
+    // The stem (Conv1d in_channel->width, no norm / activation) is only consumed by the stage-0 SA conv
+    // (and by the FPN when it climbs back to level 0): with xyz-only input it is folded into that conv.
+    const bool fold_stem = d->in_channel == 3 && d->upsample_layers < d->n_stages && group_from_xyz_supported(2 * d->width);
+    l0.fea = fold_stem ? nullptr : a.get<float>((size_t)B * N * d->width);
+    float4 *comp = fold_stem ? a.get<float4>((size_t)2 * d->width) : nullptr;
     l0.len = a.get<int>(B);
     l0.pad = nullptr;  // level-0 padding is the caller's tensor
     l0.has_grid = N >= GRID_MIN_N && N <= GRID_MAX_N;
@@ -180,7 +185,8 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
         const int K0 = d->nsample[i][0];
         const double r0 = d->radius[i][0];
         int32_t *gidx = a.get<int32_t>((size_t)B * S * K0);
-        float *Z = a.get<float>((size_t)B * src.n * Cout);
+        const bool folded = i == 0 && fold_stem;
+        float *Z = folded ? nullptr : a.get<float>((size_t)B * src.n * Cout);
         const float *Wsa = W(), *bsa = W(), *gsa = W(), *besa = W();
         if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
         if (!dry) {
@@ -200,12 +206,17 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
                 DPM_CHECK_CUDA(cudaMemcpyAsync(trace_knn + knn_off, gidx, sizeof(int32_t) * (size_t)B * S * K0,
                                                cudaMemcpyDeviceToDevice, st));
             }
-            // per-point half of the 1x1 conv: Z = fea . Wfea^T + b   (weight columns [0:Cin] = features)
-            set_unit_rows(src.n);
-            DPM_TRY(linear_launch(src.fea, Cin, Wsa, Cin + 3, bsa, nullptr, 0, Z, Cout, B * src.n, Cout, Cin,
-                                  DPM_ACT_NONE, st));
-            DPM_TRY(group_launch(Z, src.xyz, dst.xyz, gidx, Wsa + Cin, Cin + 3, gsa, besa, (float)r0, dst.fea, B, src.n, S, K0,
-                                 Cout, st));
+            if (folded) {
+                DPM_TRY(group_from_xyz_launch(Wsa, Cin + 3, bsa, W0, b0, Cin, comp, src.xyz, dst.xyz, gidx, gsa, besa, (float)r0,
+                                              dst.fea, B, src.n, S, K0, Cout, st));
+            } else {
+                // per-point half of the 1x1 conv: Z = fea . Wfea^T + b   (weight columns [0:Cin] = features)
+                set_unit_rows(src.n);
+                DPM_TRY(linear_launch(src.fea, Cin, Wsa, Cin + 3, bsa, nullptr, 0, Z, Cout, B * src.n, Cout, Cin,
+                                      DPM_ACT_NONE, st));
+                DPM_TRY(group_launch(Z, src.xyz, dst.xyz, gidx, Wsa + Cin, Cin + 3, gsa, besa, (float)r0, dst.fea, B, src.n, S, K0,
+                                     Cout, st));
+            }
         }
         fps_off += (size_t)B * S;
         knn_off += (size_t)B * S * K0;

@@ -432,6 +432,47 @@ knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted
     }
     float ld = INF, thrd = cap;  // candidates must satisfy (d, i) < (thrd, thri)
     int li = 0x7fffffff, thri = -1;
+    // Candidates that beat the current bound are appended to a per-warp staging buffer; every 32 of them
+    // are sorted across the lanes (bitonic) and merged into the running list in one go.  The bound is
+    // only refreshed at a flush, so a few candidates pass that a per-candidate insertion would have
+    // rejected -- the merge drops them, the final list is the same (d2, index)-ordered top K.
+    __shared__ float sbd[KG_T / 32][64];
+    __shared__ int sbi[KG_T / 32][64];
+    float *bd = sbd[threadIdx.x >> 5];
+    int *bi = sbi[threadIdx.x >> 5];
+    int fill = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    auto flush = [&](float cd, int ci) {
+        // sort the 32 staged candidates ascending by (d, i)
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, cd, j);
+                const int oi = __shfl_xor_sync(0xffffffffu, ci, j);
+                const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+                const bool less = od < cd || (od == cd && oi < ci);
+                if (keep_min == less) { cd = od; ci = oi; }
+            }
+        }
+        // the 32 smallest of (list U candidates): element-wise min of the list and the reversed candidates
+        // is bitonic; one bitonic merge sorts it
+        const float rd = __shfl_sync(0xffffffffu, cd, 31 - lane);
+        const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+        if (rd < ld || (rd == ld && ri < li)) { ld = rd; li = ri; }
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, ld, j);
+            const int oi = __shfl_xor_sync(0xffffffffu, li, j);
+            const bool keep_min = (lane & j) == 0;
+            const bool less = od < ld || (od == ld && oi < li);
+            if (keep_min == less) { ld = od; li = oi; }
+        }
+        if (lane >= K) { ld = INF; li = 0x7fffffff; }
+        const float kd = __shfl_sync(0xffffffffu, ld, K - 1);
+        const int ki = __shfl_sync(0xffffffffu, li, K - 1);
+        if (kd < INF) { thrd = kd; thri = ki; }
+    };
     for (int r = 0; r < 9; ++r) {
         const int st = __shfl_sync(0xffffffffu, rs, r), en = __shfl_sync(0xffffffffu, re, r);
         for (int i0 = st; i0 < en; i0 += 32) {
@@ -443,24 +484,32 @@ knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted
                 dd = d2_exact(c.x, c.y, c.z, p.x, p.y, p.z);
                 gi = __float_as_int(p.w);
             }
-            unsigned cm = __ballot_sync(0xffffffffu, dd < thrd || (dd == thrd && gi < thri));
-            while (cm) {
-                const int src = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const float dc = __shfl_sync(0xffffffffu, dd, src);
-                const int ic = __shfl_sync(0xffffffffu, gi, src);
-                if (dc < thrd || (dc == thrd && ic < thri)) {  // warp-uniform re-check against the updated bound
-                    const int pos = __popc(__ballot_sync(0xffffffffu, ld < dc || (ld == dc && li < ic)) & kmask);
-                    const float ud = __shfl_up_sync(0xffffffffu, ld, 1);
-                    const int ui = __shfl_up_sync(0xffffffffu, li, 1);
-                    if (lane > pos) { ld = ud; li = ui; }
-                    if (lane == pos) { ld = dc; li = ic; }
-                    const float kd = __shfl_sync(0xffffffffu, ld, K - 1);
-                    const int ki = __shfl_sync(0xffffffffu, li, K - 1);
-                    if (kd < INF) { thrd = kd; thri = ki; }
+            const bool pass = dd < thrd || (dd == thrd && gi < thri);
+            const unsigned cm = __ballot_sync(0xffffffffu, pass);
+            if (cm) {
+                if (pass) {
+                    const int slot = fill + __popc(cm & lt);
+                    bd[slot] = dd;
+                    bi[slot] = gi;
+                }
+                fill += __popc(cm);
+                if (fill >= 32) {
+                    __syncwarp();
+                    const float cd = bd[lane];
+                    const int ci = bi[lane];
+                    const float td = bd[32 + lane];
+                    const int ti = bi[32 + lane];
+                    __syncwarp();
+                    fill -= 32;
+                    if (lane < fill) { bd[lane] = td; bi[lane] = ti; }
+                    flush(cd, ci);
                 }
             }
         }
+    }
+    if (fill > 0) {
+        __syncwarp();
+        flush(lane < fill ? bd[lane] : INF, lane < fill ? bi[lane] : 0x7fffffff);
     }
     const int count = __popc(__ballot_sync(0xffffffffu, ld < INF) & kmask);
     const int kvalid = min(len, K);

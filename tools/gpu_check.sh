@@ -13,8 +13,8 @@ python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/${TAG}_smi.tx
 ( timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 ) > gpurun_out/${TAG}_bench_ref.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_kernel -c 1 -f -o gpurun_out/${TAG}_fps \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_grid_kernel -c 1 -f -o gpurun_out/${TAG}_fps \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_fps.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn_kernel -c 1 -f -o gpurun_out/${TAG}_knn \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:knn_grid_kernel -c 1 -f -o gpurun_out/${TAG}_knn \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_knn.log 2>&1
 cat gpurun_out/${TAG}_pytest.log gpurun_out/${TAG}_smoke.log gpurun_out/${TAG}_bench.log
