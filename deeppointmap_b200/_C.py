@@ -10,7 +10,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdpm_b200.so")
+LIB_PATH = os.environ.get("DPM_LIB") or os.path.join(_HERE, "libdpm_b200.so")  # DPM_LIB: instrumented developer build
 
 MAX_STAGES, MAX_BLOCKS = 8, 4
 REG_R, REG_T, REG_RMSE, REG_NCORR, REG_NINLIER, REG_ITERS, REG_STRIDE = 0, 9, 12, 13, 14, 15, 16

@@ -30,14 +30,21 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    # developer builds: DPM_BUILD_DEFINES="-DDPM_FPS_PROFILE" DPM_BUILD_SO=/path/libx.so (instrumented copy
+    # next to the product library; load it with DPM_LIB=/path/libx.so)
+    global SO
+    defines = os.environ.get("DPM_BUILD_DEFINES", "").split()
+    alt = os.environ.get("DPM_BUILD_SO")
+    if alt:
+        SO, force = alt, True
     if not force and not needs_build():
         return SO
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_alt" if alt else ""))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + defines + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:

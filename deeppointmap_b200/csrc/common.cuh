@@ -135,6 +135,11 @@ bool linear_tc_eligible(const float *X, int ldx, long long sX, const float *W, i
 int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
                      const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
                      int act, cudaStream_t st);
+// per-call pre-split (hi/lo tf32) copies of the weights for the tensor-core path (gemm_tc.cu)
+void split_begin();
+void split_add(Arena &a, const float *W, int rows, int cols, int ld);
+int split_run(cudaStream_t st);
+const float *split_lookup(const float *W, int rows, int cols, int ld);
 int linear_batched_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW,
                           const float *bias, const float *res, int ldres, float *Y, int ldy, long long sY, int M,
                           int N, int K, int nbatch, int act, cudaStream_t st);

@@ -740,6 +740,37 @@ static void dec_bind(const dpm_decoder_desc *d, const float *const *w, DecW &o) 
     o.dim_t = w[i++];
 }
 
+// pre-split (hi/lo tf32) copies of the weights this call pushes through the tensor-core GEMM
+static int dec_split(const dpm_decoder_desc *d, const DecW *w, bool registration, Arena &a, cudaStream_t st) {
+    const int C = d->model_channel, Cf = d->in_channel;
+    split_begin();
+    split_add(a, w ? w->proj_w : nullptr, C, Cf, Cf);
+    for (int l = 0; l < d->attention_layers; ++l) {
+        const DecW::Layer *L = w ? &w->layer[l] : nullptr;
+        split_add(a, L ? L->sa_in_w : nullptr, 3 * C, C, C);
+        split_add(a, L ? L->sa_out_w : nullptr, C, C, C);
+        split_add(a, L ? L->ca_in_w : nullptr, 3 * C, C, C);
+        split_add(a, L ? L->ca_out_w : nullptr, C, C, C);
+        split_add(a, L ? L->m0_w : nullptr, C, C, C);
+        split_add(a, L ? L->m2_w : nullptr, C, C, C);
+    }
+    if (registration) {
+        split_add(a, w ? w->sim0_w : nullptr, C, C, C);
+        split_add(a, w ? w->sim2_w : nullptr, C, C, C);
+        split_add(a, w ? w->off0_w : nullptr, C, 2 * C, 2 * C);
+        split_add(a, w ? w->off2_w : nullptr, C / 2, C, C);
+        split_add(a, w ? w->offd_w : nullptr, C / 4, 2 * C, 2 * C);
+        split_add(a, w ? w->off4_w : nullptr, C / 4, C / 2, C / 2);
+    } else {
+        split_add(a, w ? w->lp0_w : nullptr, C, C, C);
+        split_add(a, w ? w->lp2_w : nullptr, C, C, C);
+        split_add(a, w ? w->lq0_w : nullptr, 2 * C, 2 * C, 2 * C);
+    }
+    if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "decoder: workspace too small");
+    if (!a.dry) DPM_TRY(split_run(st));
+    return DPM_OK;
+}
+
 // _descriptor_attention_forward (decoder.py:145-162): -> F (R, C) correlated features, xyz (R)
 static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float *src, const float *dst, int P, int M,
                            int N, Arena &a, float **F_out, float4 **xyz_out, cudaStream_t st) {
@@ -801,6 +832,8 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     const int C = d->model_channel, R = P * (M + N), K2 = 2 * k;
     float *F = nullptr;
     float4 *xyz = nullptr;
+    if (d->attention_layers < 0 || d->attention_layers > 16) return fail(DPM_ERR_SHAPE, "decoder: attention_layers");
+    DPM_TRY(dec_split(d, dry ? nullptr : &w, true, a, st));
     DPM_TRY(attention_stack(d, w, src, dst, P, M, N, a, &F, &xyz, st));
     float *h = a.get<float>((size_t)R * C);
     float *sim = a.get<float>((size_t)R * C);
@@ -875,6 +908,8 @@ static int loop_run(const dpm_decoder_desc *d, const float *const *weights, cons
     const int C = d->model_channel, R = P * (M + N);
     float *F = nullptr;
     float4 *xyz = nullptr;
+    if (d->attention_layers < 0 || d->attention_layers > 16) return fail(DPM_ERR_SHAPE, "decoder: attention_layers");
+    DPM_TRY(dec_split(d, dry ? nullptr : &w, false, a, st));
     DPM_TRY(attention_stack(d, w, src, dst, P, M, N, a, &F, &xyz, st));
     float *h = a.get<float>((size_t)R * C);
     float *g = a.get<float>((size_t)R * C);

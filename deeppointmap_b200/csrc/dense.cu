@@ -96,8 +96,10 @@ int linear_batched_launch(const float *X, int ldx, long long sX, const float *W,
                           const float *bias, const float *res, int ldres, float *Y, int ldy, long long sY, int M,
                           int N, int K, int nbatch, int act, cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0 || nbatch <= 0) return fail(DPM_ERR_SHAPE, "linear: bad shape M=%d N=%d K=%d", M, N, K);
-    const int unit = g_unit_rows > 0 ? (g_unit_rows < M ? g_unit_rows : M) : M;
-    if (unit >= 128 && linear_tc_eligible(X, ldx, sX, W, ldw, sW, M, N, K) && (nbatch == 1 || (sY & 3) == 0))
+    // the tensor-core path is taken whenever the operand layout allows it, whatever M is (a short tile is
+    // zero-filled): the K-summation order of an output element never depends on how many rows share the
+    // launch, so a unit's result is bit-identical whatever else is batched with it.
+    if (linear_tc_eligible(X, ldx, sX, W, ldw, sW, M, N, K) && (nbatch == 1 || (sY & 3) == 0))
         return linear_tc_launch(X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, st);
     dim3 grid((M + GM - 1) / GM, (N + GN - 1) / GN, nbatch);
     prof_note((long long)M * nbatch, (long long)N * K);
@@ -468,6 +470,7 @@ extern "C" int dpm_linear_f32(const float *X, int ldx, const float *W, int ldw, 
                               int ldres, float *Y, int ldy, int M, int N, int K, int act, dpm_stream_t stream) {
     if (!X || !W || !Y) return fail(DPM_ERR_ARG, "linear: null pointer");
     set_unit_rows(0);
+    split_begin();  // no pre-split weights outside the encoder / decoder calls
     return linear_launch(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, (cudaStream_t)stream);
 }
 

@@ -139,6 +139,38 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
     int wi = 0;
     auto W = [&](void) -> const float * { return dry ? nullptr : w[wi++]; };
 
+    const bool fold_stem = d->in_channel == 3 && d->upsample_layers < d->n_stages && group_from_xyz_supported(2 * d->width);
+    // pre-split (hi/lo tf32) copies of every conv weight the tensor-core GEMM will see: one launch per call
+    split_begin();
+    {
+        int k = 2, wd = d->width;
+        auto WP = [&](int idx) -> const float * { return dry ? nullptr : w[idx]; };
+        for (int i = 0; i < d->n_stages; ++i) {
+            const int Cin = wd, Cout = 2 * wd, Ch = Cout * d->expansion;
+            if (!(i == 0 && fold_stem)) split_add(a, WP(k), Cout, Cin, Cin + 3);
+            k += 4;
+            for (int j = 1; j < d->n_blocks[i]; ++j) {
+                split_add(a, WP(k), Cout, Cout, Cout + 3);
+                split_add(a, WP(k + 4), Ch, Cout, Cout);
+                split_add(a, WP(k + 8), Cout, Ch, Ch);
+                k += 12;
+            }
+            wd *= 2;
+        }
+        int up_in = wd;
+        for (int i = 0; i < d->upsample_layers; ++i) {
+            const int up_out = d->out_channel > wd / 2 ? d->out_channel : wd / 2;
+            const int Ccat = wd / 2 + up_in;
+            split_add(a, WP(k), up_out, Ccat, Ccat);
+            split_add(a, WP(k + 4), up_out, up_out, up_out);
+            k += 8;
+            wd /= 2;
+            up_in = up_out;
+        }
+        if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
+        if (!dry) DPM_TRY(split_run(st));
+    }
+
     Level lv[DPM_MAX_STAGES + 1 + DPM_MAX_STAGES];
     int nl = 0;
     // level 0
@@ -148,7 +180,6 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
     l0.xyz = a.get<float4>((size_t)B * N);
     // The stem (Conv1d in_channel->width, no norm / activation) is only consumed by the stage-0 SA conv
     // (and by the FPN when it climbs back to level 0): with xyz-only input it is folded into that conv.
-    const bool fold_stem = d->in_channel == 3 && d->upsample_layers < d->n_stages && group_from_xyz_supported(2 * d->width);
     l0.fea = fold_stem ? nullptr : a.get<float>((size_t)B * N * d->width);
     float4 *comp = fold_stem ? a.get<float4>((size_t)2 * d->width) : nullptr;
     l0.len = a.get<int>(B);

@@ -143,11 +143,36 @@ __device__ __forceinline__ void produce_tile(const float *__restrict__ G, int ld
     }
 }
 
-template <int BN, int STAGES>
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// W tile from the PRE-SPLIT copy of the weights (hi and lo as two compact (N, K) fp32 matrices, made
+// once per call by split_weights_kernel): asynchronous 16-byte copies straight into the swizzled
+// layout, no registers, no ALU; rows / K past the matrix are zero-filled (src-size 0).
+template <int ROWS>
+__device__ __forceinline__ void produce_tile_presplit(const float *__restrict__ Ghi, const float *__restrict__ Glo, int ld,
+                                                      int rows_total, int r0, int K, int k0, unsigned hi, unsigned lo,
+                                                      int tid) {
+    constexpr int ITER = ROWS * 8 / 128;
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+        const int idx = tid + i * 128, r = idx >> 3, c = idx & 7;
+        const int gr = r0 + r, gk = k0 + c * 4;
+        const bool ok = gr < rows_total && gk < K;
+        const size_t o = ok ? (size_t)gr * ld + gk : 0;
+        const unsigned off = swz(r, c);
+        cp_async16(hi + off, Ghi + o, ok ? 16u : 0u);
+        cp_async16(lo + off, Glo + o, ok ? 16u : 0u);
+    }
+}
+
+template <int BN, int STAGES, bool PRESPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W, int ldw,
                  const float *__restrict__ bias, const float *__restrict__ res, int ldres, float *__restrict__ Y,
-                 int ldy, int M, int N, int K, int act, long long sX, long long sW, long long sY) {
+                 int ldy, int M, int N, int K, int act, long long sX, long long sW, long long sY, long long wlo_off) {
     X += (size_t)blockIdx.z * sX;
     W += (size_t)blockIdx.z * sW;
     Y += (size_t)blockIdx.z * sY;
@@ -190,8 +215,12 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
             const int s = kb % STAGES;
             mbar_wait(empty0 + 8 * s, (unsigned)(((kb / STAGES) & 1) ^ 1));
             unsigned char *st = smem + (size_t)s * STAGE_BYTES;
+            if (PRESPLIT)
+                produce_tile_presplit<BN>(W, W + wlo_off, ldw, N, n0, K, kb * BK, s32(st + 2 * A_TILE),
+                                          s32(st + 2 * A_TILE + B_TILE), ptid);
             produce_tile<BM>(X, ldx, M, m0, K, kb * BK, st, st + A_TILE, ptid);
-            produce_tile<BN>(W, ldw, N, n0, K, kb * BK, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ptid);
+            if (PRESPLIT) cp_async_wait_all();
+            else produce_tile<BN>(W, ldw, N, n0, K, kb * BK, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ptid);
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(full0 + 8 * s);
         }
@@ -272,11 +301,11 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PRESPLIT>
 static int launch_t(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
                     const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
-                    int act, cudaStream_t st) {
-    auto kern = linear_tc_kernel<BN, STAGES>;
+                    int act, long long wlo_off, cudaStream_t st) {
+    auto kern = linear_tc_kernel<BN, STAGES, PRESPLIT>;
     const size_t smem = (size_t)STAGES * (2 * A_TILE + 2 * BN * 128) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
@@ -284,7 +313,7 @@ static int launch_t(const float *X, int ldx, long long sX, const float *W, int l
         configured = true;
     }
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch);
-    kern<<<grid, THREADS, smem, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY);
+    kern<<<grid, THREADS, smem, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY, wlo_off);
     DPM_CHECK_LAUNCH("linear_tc", st);
     return DPM_OK;
 }
@@ -294,9 +323,10 @@ static int launch_t(const float *X, int ldx, long long sX, const float *W, int l
 bool linear_tc_eligible(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, int M, int N, int K) {
     static const bool off = getenv("DPM_NO_TC") != nullptr;
     if (off) return false;
-    if (M < 128 || N < 8 || K < 4) return false;
-    if ((K & 3) || (ldx & 3) || (ldw & 3) || (sX & 3) || (sW & 3)) return false;
-    if ((((uintptr_t)X) & 15) || (((uintptr_t)W) & 15)) return false;
+    if (M < 1 || N < 8 || K < 4) return false;
+    if ((K & 3) || (ldx & 3) || (sX & 3) || (((uintptr_t)X) & 15)) return false;
+    if (split_lookup(W, N, K, ldw)) return true;  // compact pre-split copy: the original layout does not matter
+    if ((ldw & 3) || (sW & 3) || (((uintptr_t)W) & 15)) return false;
     return true;
 }
 
@@ -304,12 +334,81 @@ int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int 
                      const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
                      int act, cudaStream_t st) {
     prof_note((long long)M * nbatch, (long long)N * K);
-#define DPM_TC_ARGS X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, st
-    if (N <= 32) return tc::launch_t<32, 4>(DPM_TC_ARGS);
-    if (N <= 64) return tc::launch_t<64, 4>(DPM_TC_ARGS);
-    if (N <= 128) return tc::launch_t<128, 3>(DPM_TC_ARGS);
-    return tc::launch_t<256, 2>(DPM_TC_ARGS);
+    // pre-split weights registered for this call (split_weights_*): hi at the returned pointer, lo right after
+    const float *Ws = (nbatch == 1) ? split_lookup(W, N, K, ldw) : nullptr;
+    if (Ws) {
+        const long long lo = (long long)N * K;
+#define DPM_TC_ARGS X, ldx, sX, Ws, K, 0, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, lo, st
+        if (N <= 32) return tc::launch_t<32, 4, true>(DPM_TC_ARGS);
+        if (N <= 64) return tc::launch_t<64, 4, true>(DPM_TC_ARGS);
+        if (N <= 128) return tc::launch_t<128, 3, true>(DPM_TC_ARGS);
+        return tc::launch_t<256, 2, true>(DPM_TC_ARGS);
 #undef DPM_TC_ARGS
+    }
+#define DPM_TC_ARGS X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, 0, st
+    if (N <= 32) return tc::launch_t<32, 4, false>(DPM_TC_ARGS);
+    if (N <= 64) return tc::launch_t<64, 4, false>(DPM_TC_ARGS);
+    if (N <= 128) return tc::launch_t<128, 3, false>(DPM_TC_ARGS);
+    return tc::launch_t<256, 2, false>(DPM_TC_ARGS);
+#undef DPM_TC_ARGS
+}
+
+// ---------------------------------------------------------------------------------------
+// per-call weight split: every 2-D weight the call will push through the tensor-core path is split ONCE
+// into compact hi / lo tf32 matrices in the caller's workspace (one launch for all of them), instead of
+// once per CTA per K block inside the GEMM.
+// ---------------------------------------------------------------------------------------
+constexpr int SPLIT_MAX = 56;
+struct SplitJob {
+    const float *src;
+    float *dst;
+    int rows, cols, ld, pad;
+};
+struct SplitTable {
+    SplitJob job[SPLIT_MAX];
+};
+static thread_local SplitTable g_split;
+static thread_local int g_nsplit = 0;
+
+__global__ void __launch_bounds__(256) split_weights_kernel(const __grid_constant__ SplitTable t) {
+    const SplitJob j = t.job[blockIdx.y];
+    const int n = j.rows * j.cols;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int r = i / j.cols, c = i - r * j.cols;
+        const float v = j.src[(size_t)r * j.ld + c];
+        const float h = tc::tf32_rna(v);
+        j.dst[i] = h;
+        j.dst[(size_t)n + i] = tc::tf32_rna(v - h);
+    }
+}
+
+void split_begin() { g_nsplit = 0; }
+
+void split_add(Arena &a, const float *W, int rows, int cols, int ld) {
+    if (rows < 8 || cols < 4 || (cols & 3)) return;  // never taken by the tensor-core path
+    float *dst = a.get<float>((size_t)2 * rows * cols);
+    if (a.dry || !dst || !W || g_nsplit >= SPLIT_MAX) return;
+    SplitJob &j = g_split.job[g_nsplit++];
+    j.src = W; j.dst = dst; j.rows = rows; j.cols = cols; j.ld = ld; j.pad = 0;
+}
+
+int split_run(cudaStream_t st) {
+    if (g_nsplit == 0) return DPM_OK;
+    int maxn = 0;
+    for (int i = 0; i < g_nsplit; ++i) maxn = g_split.job[i].rows * g_split.job[i].cols > maxn ? g_split.job[i].rows * g_split.job[i].cols : maxn;
+    int gx = (maxn + 1023) / 1024;  // ~4 elements per thread for the largest matrix
+    gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+    split_weights_kernel<<<dim3(gx, g_nsplit, 1), 256, 0, st>>>(g_split);
+    DPM_CHECK_LAUNCH("split_weights", st);
+    return DPM_OK;
+}
+
+const float *split_lookup(const float *W, int rows, int cols, int ld) {
+    for (int i = 0; i < g_nsplit; ++i) {
+        const SplitJob &j = g_split.job[i];
+        if (j.src == W && j.rows == rows && j.cols == cols && j.ld == ld) return j.dst;
+    }
+    return nullptr;
 }
 
 }  // namespace dpm

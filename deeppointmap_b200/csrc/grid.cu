@@ -212,11 +212,14 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 
 // ---------------------------------------------------------------------------------------
 // pruned exact FPS: one CTA (32 warps) per cloud; bucket b is owned by lane b/32 of warp b%32
-// so that spatially adjacent buckets are spread over different warps.
+// so that spatially adjacent buckets are spread over different warps.  A warp with several
+// touched buckets issues the loads of up to DEPTH of them before consuming the first, so a
+// round costs one L2 round trip.  (A shared-memory work queue that spreads the touched buckets
+// over all warps was measured too: 2 more barriers per pick cost what the balance gains.)
 // ---------------------------------------------------------------------------------------
 constexpr int FG_T = 1024;
 
-template <int PPL>
+template <int PPL, int DEPTH>
 __global__ void __launch_bounds__(FG_T, 1)
 fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
                 const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
@@ -299,36 +302,51 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
         }
         unsigned mask = __ballot_sync(0xffffffffu, act);
         while (mask) {
-            const int L = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int base = (L * 32 + warp) * BS + lane;
-            float bestv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
-            unsigned besti = 0xffffffffu;
-            float4 p[PPL];
-            float m[PPL];
+            // up to DEPTH touched buckets of this warp per round: all their loads are issued before the
+            // first one is consumed, so a round costs one L2 round trip
+            int Ls[DEPTH];
+            float4 p[DEPTH][PPL];
+            float m[DEPTH][PPL];
 #pragma unroll
-            for (int j = 0; j < PPL; ++j) {
-                p[j] = P[base + j * 32];
-                m[j] = M[base + j * 32];
-            }
+            for (int d = 0; d < DEPTH; ++d) {
+                Ls[d] = -1;
+                if (mask) {
+                    Ls[d] = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int base = (Ls[d] * 32 + warp) * BS + lane;
 #pragma unroll
-            for (int j = 0; j < PPL; ++j) {
-                const float d = d2_exact(sx, sy, sz, p[j].x, p[j].y, p[j].z);
-                const float nm = fminf(m[j], d);
-                if (nm < m[j]) M[base + j * 32] = nm;
-                const unsigned id = __float_as_uint(p[j].w);
-                if (nm > bestv || (nm == bestv && id < besti)) {
-                    bestv = nm; besti = id; bx = p[j].x; by = p[j].y; bz = p[j].z;
+                    for (int j = 0; j < PPL; ++j) {
+                        p[d][j] = P[base + j * 32];
+                        m[d][j] = M[base + j * 32];
+                    }
                 }
             }
-            const unsigned bits = __float_as_uint(bestv);  // bestv >= 0: the bit pattern is order preserving
-            const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
-            const unsigned wmin = __reduce_min_sync(0xffffffffu, bits == wmax ? besti : 0xffffffffu);
-            const int src = __ffs(__ballot_sync(0xffffffffu, bits == wmax && besti == wmin)) - 1;
-            const float wx = __shfl_sync(0xffffffffu, bx, src);
-            const float wy = __shfl_sync(0xffffffffu, by, src);
-            const float wz = __shfl_sync(0xffffffffu, bz, src);
-            if (lane == L) { maxbits = wmax; argidx = wmin; ax = wx; ay = wy; az = wz; }
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                if (Ls[d] < 0) break;  // warp-uniform
+                const int L = Ls[d];
+                const int base = (L * 32 + warp) * BS + lane;
+                float bestv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+                unsigned besti = 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < PPL; ++j) {
+                    const float dd = d2_exact(sx, sy, sz, p[d][j].x, p[d][j].y, p[d][j].z);
+                    const float nm = fminf(m[d][j], dd);
+                    if (nm < m[d][j]) M[base + j * 32] = nm;
+                    const unsigned id = __float_as_uint(p[d][j].w);
+                    if (nm > bestv || (nm == bestv && id < besti)) {
+                        bestv = nm; besti = id; bx = p[d][j].x; by = p[d][j].y; bz = p[d][j].z;
+                    }
+                }
+                const unsigned bits = __float_as_uint(bestv);  // bestv >= 0: the bit pattern is order preserving
+                const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+                const unsigned wmin = __reduce_min_sync(0xffffffffu, bits == wmax ? besti : 0xffffffffu);
+                const int src = __ffs(__ballot_sync(0xffffffffu, bits == wmax && besti == wmin)) - 1;
+                const float wx = __shfl_sync(0xffffffffu, bx, src);
+                const float wy = __shfl_sync(0xffffffffu, by, src);
+                const float wz = __shfl_sync(0xffffffffu, bz, src);
+                if (lane == L) { maxbits = wmax; argidx = wmin; ax = wx; ay = wy; az = wz; }
+            }
         }
         // ---- arg-max over all buckets: (value desc, original index asc) -------------------------
         const unsigned vb = owns ? maxbits : 0u;
@@ -373,8 +391,8 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
     prof_note(N, K);
 #define DPM_FG_CASE(p)                                                                                       \
     case p:                                                                                                  \
-        fps_grid_kernel<p><<<B, FG_T, 0, st>>>(g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, \
-                                               new_pad, new_len32);                                          \
+        fps_grid_kernel<p, (p <= 2 ? 2 : 1)><<<B, FG_T, 0, st>>>(g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, \
+                                                  new_pad, new_len32);                                       \
         break;
     switch (ppl) {
         DPM_FG_CASE(1) DPM_FG_CASE(2) DPM_FG_CASE(4) DPM_FG_CASE(8)
