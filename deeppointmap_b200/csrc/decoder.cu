@@ -7,6 +7,8 @@
 // self/cross attention are one launch over 2P (query-range, key-range) problems.
 // Data-dependent shapes of the reference (offset filter, sigma clipping) are restated with
 // counts + masks on the device: there is no host sync anywhere in here.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dpm {
@@ -194,6 +196,181 @@ attention_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// the same attention on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 error
+// compensation (x = hi + lo, products hi*hi + hi*lo + lo*hi), fp32 accumulation, flash-style
+// online softmax in registers.  CTA = 128 queries (8 warps x 16 rows) x one head; keys / values
+// are staged 64 at a time in shared memory already split into hi / lo (row stride 36 floats:
+// conflict-free fragment loads).  S = Q K^T accumulates in the C fragments; those registers ARE the
+// A fragments of P V once the 8 keys of a k-step are taken in the order (0,2,4,6,1,3,5,7), which
+// only changes which V rows are loaded into the B fragment.
+// ---------------------------------------------------------------------------------------
+constexpr int AT_BQ = 128, AT_BK = 64, AT_LD = 36;
+
+__device__ __forceinline__ unsigned tf32_bits(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2)
+attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__ Kp, int ldk,
+                    const float *__restrict__ Vp, int ldv, float *__restrict__ O, int ldo, const int *__restrict__ prob,
+                    int M, int N, int mode) {
+    __shared__ __align__(16) unsigned Kh[AT_BK * AT_LD], Kl[AT_BK * AT_LD], Vh[AT_BK * AT_LD], Vl[AT_BK * AT_LD];
+    const int z = blockIdx.z, head = blockIdx.y;
+    int q0, Lq, k0, Lk;
+    if (prob) {
+        q0 = prob[4 * z]; Lq = prob[4 * z + 1]; k0 = prob[4 * z + 2]; Lk = prob[4 * z + 3];
+    } else {
+        const int p = z >> 1, side = z & 1, base = p * (M + N);
+        q0 = base + (side ? M : 0);
+        Lq = side ? N : M;
+        const int kvside = mode ? !side : side;  // mode 0: self, 1: cross
+        k0 = base + (kvside ? M : 0);
+        Lk = kvside ? N : M;
+    }
+    if (blockIdx.x * AT_BQ >= Lq) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * AT_BQ + warp * 16;  // this warp's 16 query rows
+    const float NEG = -__int_as_float(0x7f800000);
+
+    // Q fragments (scaled by 1/sqrt(d) first, as nn.MultiheadAttention does), split once
+    unsigned qh[4][4], ql[4][4];
+    {
+        const float scale = 0.17677669529663687f;
+        const int ra = min(r0 + g, Lq - 1), rb = min(r0 + g + 8, Lq - 1);
+        const float *qa = Q + (size_t)(q0 + ra) * ldq + head * 32, *qb = Q + (size_t)(q0 + rb) * ldq + head * 32;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float v[4] = {qa[8 * s + t] * scale, qb[8 * s + t] * scale, qa[8 * s + t + 4] * scale,
+                                qb[8 * s + t + 4] * scale};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                qh[s][i] = tf32_bits(v[i]);
+                ql[s][i] = tf32_bits(v[i] - __uint_as_float(qh[s][i]));
+            }
+        }
+    }
+    float oh[4][4], ox[4][4];  // O accumulators: hi*hi terms / cross terms (kept apart: the MMA's fp32 add truncates)
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { oh[d][i] = 0.f; ox[d][i] = 0.f; }
+    float m0 = NEG, m1 = NEG, l0 = 0.f, l1 = 0.f;  // rows g and g+8; l is this thread's partial row sum
+
+    for (int c0 = 0; c0 < Lk; c0 += AT_BK) {
+        __syncthreads();
+        for (int e = tid; e < AT_BK * 8; e += 256) {
+            const int key = e >> 3, part = e & 7;
+            float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+            if (c0 + key < Lk) {
+                const size_t row = (size_t)(k0 + c0 + key);
+                kk = *reinterpret_cast<const float4 *>(Kp + row * ldk + head * 32 + 4 * part);
+                vv = *reinterpret_cast<const float4 *>(Vp + row * ldv + head * 32 + 4 * part);
+            }
+            uint4 h, l;
+            h.x = tf32_bits(kk.x); l.x = tf32_bits(kk.x - __uint_as_float(h.x));
+            h.y = tf32_bits(kk.y); l.y = tf32_bits(kk.y - __uint_as_float(h.y));
+            h.z = tf32_bits(kk.z); l.z = tf32_bits(kk.z - __uint_as_float(h.z));
+            h.w = tf32_bits(kk.w); l.w = tf32_bits(kk.w - __uint_as_float(h.w));
+            *reinterpret_cast<uint4 *>(&Kh[key * AT_LD + 4 * part]) = h;
+            *reinterpret_cast<uint4 *>(&Kl[key * AT_LD + 4 * part]) = l;
+            h.x = tf32_bits(vv.x); l.x = tf32_bits(vv.x - __uint_as_float(h.x));
+            h.y = tf32_bits(vv.y); l.y = tf32_bits(vv.y - __uint_as_float(h.y));
+            h.z = tf32_bits(vv.z); l.z = tf32_bits(vv.z - __uint_as_float(h.z));
+            h.w = tf32_bits(vv.w); l.w = tf32_bits(vv.w - __uint_as_float(h.w));
+            *reinterpret_cast<uint4 *>(&Vh[key * AT_LD + 4 * part]) = h;
+            *reinterpret_cast<uint4 *>(&Vl[key * AT_LD + 4 * part]) = l;
+        }
+        __syncthreads();
+
+        // ---- S = Q K^T for 16 rows x 64 keys: sc[j] = keys 8j..8j+7 ----
+        float sc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int o = (8 * j + g) * AT_LD + 8 * s + t;
+                const unsigned b0h = Kh[o], b1h = Kh[o + 4], b0l = Kl[o], b1l = Kl[o + 4];
+                mma_tf32_16n8k8(sc[j], ql[s], b0h, b1h);
+                mma_tf32_16n8k8(sc[j], qh[s], b0l, b1l);
+                mma_tf32_16n8k8(sc[j], qh[s], b0h, b1h);
+            }
+        }
+        const int nvalid = Lk - c0;
+        if (nvalid < AT_BK) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (8 * j + 2 * t >= nvalid) { sc[j][0] = NEG; sc[j][2] = NEG; }
+                if (8 * j + 2 * t + 1 >= nvalid) { sc[j][1] = NEG; sc[j][3] = NEG; }
+            }
+        }
+        // ---- online softmax ----
+        float mx0 = NEG, mx1 = NEG;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float corr0 = expf(m0 - mn0), corr1 = expf(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        l0 *= corr0; l1 *= corr1;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            oh[d][0] *= corr0; oh[d][1] *= corr0; oh[d][2] *= corr1; oh[d][3] *= corr1;
+            ox[d][0] *= corr0; ox[d][1] *= corr0; ox[d][2] *= corr1; ox[d][3] *= corr1;
+        }
+        // ---- O += P V, 8 keys per k-step; k index t <-> key 2t, k index t+4 <-> key 2t+1 ----
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float p0 = expf(sc[j][0] - mn0), p1 = expf(sc[j][1] - mn0);
+            const float p2 = expf(sc[j][2] - mn1), p3 = expf(sc[j][3] - mn1);
+            l0 += p0 + p1;
+            l1 += p2 + p3;
+            unsigned ph[4], pl[4];
+            ph[0] = tf32_bits(p0); pl[0] = tf32_bits(p0 - __uint_as_float(ph[0]));  // (row g,   key 2t)
+            ph[1] = tf32_bits(p2); pl[1] = tf32_bits(p2 - __uint_as_float(ph[1]));  // (row g+8, key 2t)
+            ph[2] = tf32_bits(p1); pl[2] = tf32_bits(p1 - __uint_as_float(ph[2]));  // (row g,   key 2t+1)
+            ph[3] = tf32_bits(p3); pl[3] = tf32_bits(p3 - __uint_as_float(ph[3]));  // (row g+8, key 2t+1)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int o = (8 * j + 2 * t) * AT_LD + 8 * d + g;
+                const unsigned b0h = Vh[o], b1h = Vh[o + AT_LD], b0l = Vl[o], b1l = Vl[o + AT_LD];
+                mma_tf32_16n8k8(oh[d], ph, b0h, b1h);
+                mma_tf32_16n8k8(ox[d], ph, b0l, b1l);
+                mma_tf32_16n8k8(ox[d], pl, b0h, b1h);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        if (ra < Lq)
+            *reinterpret_cast<float2 *>(O + (size_t)(q0 + ra) * ldo + head * 32 + 8 * d + 2 * t) =
+                make_float2((oh[d][0] + ox[d][0]) / l0, (oh[d][1] + ox[d][1]) / l0);
+        if (rb < Lq)
+            *reinterpret_cast<float2 *>(O + (size_t)(q0 + rb) * ldo + head * 32 + 8 * d + 2 * t) =
+                make_float2((oh[d][2] + ox[d][2]) / l1, (oh[d][3] + ox[d][3]) / l1);
+    }
+}
+
 int attention_launch(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out, int ldo,
                      const int *prob, int nprob, int maxLq, int M, int N, int mode, int heads, cudaStream_t st) {
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
@@ -203,6 +380,13 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
     if (!configured) {
         DPM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
+    }
+    static const bool simt = getenv("DPM_ATT_SIMT") != nullptr;  // developer A/B switch
+    if (!simt) {
+        dim3 gtc((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
+        attention_tc_kernel<<<gtc, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
+        DPM_CHECK_LAUNCH("attention", st);
+        return DPM_OK;
     }
     dim3 grid((maxLq + 31) / 32, heads, nprob);
     attention_kernel<<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
