@@ -15,7 +15,8 @@ int fail(int code, const char *fmt, ...);
 // counts the launch; when a profile is open (dpm_prof_begin) also records a CUDA event on `st`
 // so consecutive events bracket each kernel (everything of one call is on one stream).
 void count_launch(const char *tag, cudaStream_t st);
-void prof_note(long long a, long long b);  // detail columns of the NEXT launch record
+void prof_note(long long a, long long b);
+void prof_mark(cudaStream_t st);  // call boundary: time since the previous record is not kernel time  // detail columns of the NEXT launch record
 
 #define DPM_CHECK_CUDA(expr)                                                                   \
     do {                                                                                       \

@@ -39,9 +39,19 @@ void prof_note(long long a, long long b) {
     g_note_b = b;
 }
 
+static void prof_record(const char *tag, cudaStream_t st);
+
 void count_launch(const char *tag, cudaStream_t st) {
     ++g_launches;
-    if (!g_prof_on) return;
+    if (g_prof_on) prof_record(tag, st);
+}
+
+// start of a C-ABI call: the stream time since the previous record is host-side gap, not kernel time
+void prof_mark(cudaStream_t st) {
+    if (g_prof_on) prof_record("host_gap", st);
+}
+
+static void prof_record(const char *tag, cudaStream_t st) {
     if (g_prof_n == g_prof_cap) {
         const int ncap = g_prof_cap ? g_prof_cap * 2 : 1024;
         ProfRec *np = (ProfRec *)realloc(g_prof, sizeof(ProfRec) * ncap);

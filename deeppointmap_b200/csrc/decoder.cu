@@ -1137,6 +1137,7 @@ extern "C" int dpm_registration_forward(const dpm_decoder_desc *desc, const floa
     if (!desc || !weights || !src || !dst || !result || !conf_out || !ws) return fail(DPM_ERR_ARG, "registration: null pointer");
     if (n_weights != dec_num_weights(desc) + 1)
         return fail(DPM_ERR_SHAPE, "registration: got %d weight tensors, expected %d", n_weights, dec_num_weights(desc) + 1);
+    prof_mark((cudaStream_t)stream);
     Arena a(ws, ws_bytes);
     return registration_run(desc, weights, src, dst, P, M, N, k, result, conf_out, a, (cudaStream_t)stream);
 }
@@ -1154,6 +1155,7 @@ extern "C" int dpm_loop_detection_forward(const dpm_decoder_desc *desc, const fl
     if (!desc || !weights || !src || !dst || !prob || !ws) return fail(DPM_ERR_ARG, "loop_detection: null pointer");
     if (n_weights != dec_num_weights(desc) + 1)
         return fail(DPM_ERR_SHAPE, "loop_detection: got %d weight tensors, expected %d", n_weights, dec_num_weights(desc) + 1);
+    prof_mark((cudaStream_t)stream);
     Arena a(ws, ws_bytes);
     return loop_run(desc, weights, src, dst, P, M, N, prob, a, (cudaStream_t)stream);
 }

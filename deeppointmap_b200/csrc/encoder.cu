@@ -369,6 +369,7 @@ extern "C" int dpm_encoder_forward(const dpm_encoder_desc *desc, const float *co
                                    dpm_stream_t stream) {
     if (!desc || !weights || !points || !ws) return fail(DPM_ERR_ARG, "encoder: null pointer");
     if (B <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "encoder: bad shape B=%d N=%d", B, N);
+    prof_mark((cudaStream_t)stream);
     Arena a(ws, ws_bytes);
     return encoder_run(desc, weights, n_weights, points, C, padding, B, N, out_coor, out_fea, out_pad, desc_out,
                        coor_scale, trace_fps, trace_knn, a, (cudaStream_t)stream);

@@ -224,14 +224,20 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(full0 + 8 * s);
         }
-        // ================= epilogue: one output row per thread =================
+        // ================= epilogue =================
+        // tcgen05.ld hands thread t of a warp row (lane quarter base + t); writing rows from there would
+        // touch 32 different 128-byte lines per instruction (and so would the residual read).  The 32x32
+        // chunk goes through shared memory instead (the pipeline stages are idle by now) and leaves /
+        // meets the residual as whole 128-byte row segments, 4 rows per warp instruction.
         mbar_wait(accum, 0u);
         tc_fence_after();
         const int quarter = warp & 3;  // the TMEM lane quarter this warp may read
-        const int row = m0 + quarter * 32 + lane;
         constexpr int CHALF = BN >= 64 ? BN / 2 : BN;  // columns per producer group in the epilogue
+        constexpr int TLD = 36;                        // staging row stride (floats): 16-byte aligned, conflict-free
+        float *tb = reinterpret_cast<float *>(smem) + warp * (32 * TLD);
         const bool vec = ((ldy & 3) == 0) && ((((uintptr_t)Y) & 15) == 0) && (!bias || ((((uintptr_t)bias) & 15) == 0)) &&
                          (!res || (((ldres & 3) == 0) && ((((uintptr_t)res) & 15) == 0)));
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // this lane's (row within a group of 4, column) when storing
 #pragma unroll 1
         for (int cb = grp * CHALF; cb < (BN >= 64 ? (grp + 1) * CHALF : (grp == 0 ? BN : 0)); cb += 32) {
             if (n0 + cb >= N) break;  // warp-uniform
@@ -239,38 +245,44 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
             tmem_ld32(tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)cb, v);
             tmem_ld32(tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)(BN + cb), vc);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] += vc[c];
-            if (row < M) {
-                float *yr = Y + (size_t)row * ldy + n0 + cb;
-                const float *rr = res ? res + (size_t)row * ldres + n0 + cb : nullptr;
-                if (vec && n0 + cb + 32 <= N) {
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4 *>(tb + lane * TLD + 4 * q) =
+                    make_float4(v[4 * q] + vc[4 * q], v[4 * q + 1] + vc[4 * q + 1], v[4 * q + 2] + vc[4 * q + 2],
+                                v[4 * q + 3] + vc[4 * q + 3]);
+            __syncwarp();
+            const int col = n0 + cb + c4;
+            if (vec && n0 + cb + 32 <= N) {
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
+                float4 r4[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (bias) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + n0 + cb) + q);
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                        }
-                        if (rr) {
-                            const float4 r4 = *(reinterpret_cast<const float4 *>(rr) + q);
-                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-                        }
-                        if (act == DPM_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *(reinterpret_cast<float4 *>(yr) + q) = o;
-                    }
-                } else {
+                for (int i = 0; i < 8; ++i) {
+                    const int row = m0 + quarter * 32 + i * 4 + rsub;
+                    r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (res && row < M) r4[i] = *reinterpret_cast<const float4 *>(res + (size_t)row * ldres + col);
+                }
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        if (n0 + cb + c < N) {
-                            float o = v[c];
-                            if (bias) o += bias[n0 + cb + c];
-                            if (rr) o += rr[c];
-                            if (act == DPM_ACT_RELU) o = fmaxf(o, 0.f);
-                            yr[c] = o;
-                        }
+                for (int i = 0; i < 8; ++i) {
+                    const int row = m0 + quarter * 32 + i * 4 + rsub;
+                    float4 o = *reinterpret_cast<const float4 *>(tb + (i * 4 + rsub) * TLD + c4);
+                    o.x += bb.x + r4[i].x; o.y += bb.y + r4[i].y; o.z += bb.z + r4[i].z; o.w += bb.w + r4[i].w;
+                    if (act == DPM_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (row < M) *reinterpret_cast<float4 *>(Y + (size_t)row * ldy + col) = o;
+                }
+            } else {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int row = m0 + quarter * 32 + r, cc = n0 + cb + lane;
+                    if (row < M && cc < N) {
+                        float o = tb[r * TLD + lane];
+                        if (bias) o += bias[cc];
+                        if (res) o += res[(size_t)row * ldres + cc];
+                        if (act == DPM_ACT_RELU) o = fmaxf(o, 0.f);
+                        Y[(size_t)row * ldy + cc] = o;
                     }
                 }
             }
+            __syncwarp();
         }
     } else if (lane == 0) {
         // ================= MMA issuer: one thread =================
