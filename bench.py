@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-batch1", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (0 = auto)")
     ap.add_argument("--kernels", type=int, default=16, help="entries of the per-kernel breakdown to print")
     return ap.parse_args()
@@ -112,7 +113,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self.nv is not None:
@@ -369,6 +370,32 @@ def main():
                    "api": "Encoder.descriptors + Decoder.registration_forward_batch (one C-ABI call each), pinned host "
                           "input, pose records copied back to pinned memory every step"}
 
+        # ---- batch 1 (BASELINE.json configs[1]/[2]): one frame + one registration at a time, one stream ----
+        batch1 = None
+        if not args.no_batch1:
+            db1 = torch.zeros((2, Cd, S), dtype=torch.float32, device=dev)
+            one = [dev_pool[s % nslots][(3 * s) % F:(3 * s) % F + 1].contiguous() for s in range(min(16, 4 * nslots))]
+
+            def step1(i):
+                enc.descriptors(one[i % len(one)], None, coor_scale=cfg.coor_scale, out=db1[1:])
+                r1, _ = dec.registration_forward_batch(db1[:1], db1[1:], 0.5)
+                db1[0].copy_(db1[1])
+                return r1
+
+            for i in range(3):
+                step1(i)
+            torch.cuda.synchronize()
+            n1 = 20
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for i in range(n1):
+                step1(3 + i)
+            b1.record()
+            torch.cuda.synchronize()
+            ms1 = b0.elapsed_time(b1) / n1
+            batch1 = {"frames_per_s": 1e3 / ms1, "ms_per_frame": ms1, "streams": 1, "frames_per_step": 1,
+                      "note": "latency-bound: 4095 + 1023 + 255 + 63 + 15 sequential FPS picks per frame"}
+
         # ---- per-kernel profile pass (CUDA events after every launch, same stream) ---------
         prof_steps = 3
         agg = {}
@@ -457,7 +484,7 @@ def main():
                    "frames_per_gpu_per_step": F, "points_per_frame": n, "global_frames_per_step": world * F,
                    "parallelism": f"frame-parallel x{world}", "streams_per_gpu": NS,
                    "l2": f"inputs rotate over a {pool_mb:.0f} MiB pool of {nslots} batches per GPU (> 126 MB L2)"},
-        "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / K,
+        "e2e": e2e, "batch1": batch1, "gpu_launches": int(launches), "launches_per_step": launches / K,
         "clocks": clk.summary(), "roofline": roofline,
         "index_ops": {"fps_plus_knn_GBps": idx_gbps, "frac_of_peak": idx_gbps / peak if idx_gbps else None,
                       "algorithmic_bytes_per_frame": idx_bytes, "fps_ms_per_step": fps_ms, "knn_ms_per_step": knn_ms,
@@ -470,9 +497,10 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         frames = args.cpu_frames or max(1, min(8, cores // 4))
-        r = run_cpu_sample(cfg, n, frames, 2, 1)
+        cpu_steps = 16  # ~10-20 s of host work on a 16-core box
+        r = run_cpu_sample(cfg, n, frames, cpu_steps, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                "sample": f"2 steps x {frames} frames x {n} pts (encoder + {frames} registrations each) after 1 "
+                                "sample": f"{cpu_steps} steps x {frames} frames x {n} pts (encoder + {frames} registrations each) after 1 "
                                           f"warm-up step, oracle port (torch fp32 + C/OpenMP index ops), {r['seconds']:.1f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
