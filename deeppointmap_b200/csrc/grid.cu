@@ -211,67 +211,78 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 }
 
 // ---------------------------------------------------------------------------------------
-// pruned exact FPS: one CTA (32 warps) per cloud; bucket b is owned by lane b/32 of warp b%32
-// so that spatially adjacent buckets are spread over different warps.  A warp with several
-// touched buckets issues the loads of up to DEPTH of them before consuming the first, so a
-// round costs one L2 round trip.  (A shared-memory work queue that spreads the touched buckets
-// over all warps was measured too: 2 more barriers per pick cost what the balance gains.)
+// pruned exact FPS: one CTA of T threads per cloud.  The <= 1024 buckets are dealt round-robin
+// over the W = T/32 warps (bucket s*T + lane*W + warp is slot s of that lane), so the buckets a
+// new sample touches -- spatial neighbours, i.e. consecutive ids -- spread over all warps.  An
+// owner keeps its buckets' boxes, largest min-distances and the points attaining them in
+// registers.  Per pick: every owner tests its 1024/T boxes; a warp then updates its touched
+// buckets, one per slot per round with all loads of a round in flight together (one L2 round
+// trip per round); warp arg-max -> shared memory -> one barrier -> every warp reduces the W
+// records.  Measured on B200 (N = 65536, K = 4096): T = 1024 / 512 / 256 / 128 -> 4.98 / 5.3 /
+// 7.1 / 11.3 ms -- a pick is bound by the dependent-instruction latency of ONE warp's chain
+// (test, load, update, reduce), so one bucket per thread wins; 2048 buckets of 32 points (two per
+// thread) lose 17 %, and a shared-memory work queue that balances the touched buckets over the
+// warps costs two more barriers per pick, which is what the balance gains.
 // ---------------------------------------------------------------------------------------
-constexpr int FG_T = 1024;
-
-template <int PPL, int DEPTH>
-__global__ void __launch_bounds__(FG_T, 1)
+template <int PPL, int T, int BPT>
+__global__ void __launch_bounds__(T, 1)
 fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
                 const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
                 int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
                 uint8_t *__restrict__ new_pad, int *__restrict__ new_len32) {
-    constexpr int BS = 32 * PPL;
-    __shared__ unsigned long long skey[2][32];
-    __shared__ float4 sxyz[2][32];
+    constexpr int BS = 32 * PPL, W = T / 32;
+    __shared__ unsigned long long skey[2][W];
+    __shared__ float4 sxyz[2][W];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int len = desc[b].nvalid;
     const int kn = min(len, K);
-    const int nb = (len + BS - 1) / BS;  // <= 1024
+    const int nb = (len + BS - 1) / BS;  // <= T * BPT
     const float4 *P = sorted + (size_t)b * npad;
     float *M = mind + (size_t)b * npad;
     const size_t ob = (size_t)b * K;
     const float INF = __int_as_float(0x7f800000);
-    const int mybucket = lane * 32 + warp;
-    const bool owns = mybucket < nb;
 
     // ---- prologue: bucket boxes, min-distances = +inf (sentinels 0) -------------------------
-    float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f;  // owner's bucket box
-    unsigned maxbits = 0u, argidx = 0xffffffffu;
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    for (int L = 0; L * 32 + warp < nb; ++L) {
-        const int bk = L * 32 + warp;
-        float l0 = INF, l1 = INF, l2 = INF, h0 = -INF, h1 = -INF, h2 = -INF;
-        unsigned mi = 0xffffffffu;
+    float lox[BPT], loy[BPT], loz[BPT], hix[BPT], hiy[BPT], hiz[BPT], ax[BPT], ay[BPT], az[BPT];
+    unsigned maxbits[BPT], argidx[BPT];
+    bool owns[BPT];
 #pragma unroll
-        for (int j = 0; j < PPL; ++j) {
-            const int i = bk * BS + j * 32 + lane;
-            const float4 p = P[i];
-            const unsigned id = __float_as_uint(p.w);
-            const bool valid = id != 0x7fffffffu;
-            M[i] = valid ? INF : 0.f;
-            if (valid) {
-                l0 = fminf(l0, p.x); h0 = fmaxf(h0, p.x);
-                l1 = fminf(l1, p.y); h1 = fmaxf(h1, p.y);
-                l2 = fminf(l2, p.z); h2 = fmaxf(h2, p.z);
-                mi = min(mi, id);
+    for (int s = 0; s < BPT; ++s) {
+        lox[s] = loy[s] = loz[s] = hix[s] = hiy[s] = hiz[s] = ax[s] = ay[s] = az[s] = 0.f;
+        maxbits[s] = 0u;
+        argidx[s] = 0xffffffffu;
+        owns[s] = s * T + lane * W + warp < nb;
+        for (int L = 0; L < 32; ++L) {
+            const int bk = s * T + L * W + warp;
+            if (bk >= nb) break;  // warp-uniform
+            float l0 = INF, l1 = INF, l2 = INF, h0 = -INF, h1 = -INF, h2 = -INF;
+            unsigned mi = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                const int i = bk * BS + j * 32 + lane;
+                const float4 p = P[i];
+                const unsigned id = __float_as_uint(p.w);
+                const bool valid = id != 0x7fffffffu;
+                M[i] = valid ? INF : 0.f;
+                if (valid) {
+                    l0 = fminf(l0, p.x); h0 = fmaxf(h0, p.x);
+                    l1 = fminf(l1, p.y); h1 = fmaxf(h1, p.y);
+                    l2 = fminf(l2, p.z); h2 = fmaxf(h2, p.z);
+                    mi = min(mi, id);
+                }
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, o)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, o));
-            l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o));
-            l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
-        }
-        mi = __reduce_min_sync(0xffffffffu, mi);
-        if (lane == L) {
-            lox = l0; loy = l1; loz = l2; hix = h0; hiy = h1; hiz = h2;
-            maxbits = 0x7f800000u;  // +inf: every bucket is touched by the first sample
-            argidx = mi;
+            for (int o = 16; o > 0; o >>= 1) {
+                l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, o)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+                l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o));
+                l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
+            }
+            mi = __reduce_min_sync(0xffffffffu, mi);
+            if (lane == L) {
+                lox[s] = l0; loy[s] = l1; loz[s] = l2; hix[s] = h0; hiy[s] = h1; hiz[s] = h2;
+                maxbits[s] = 0x7f800000u;  // +inf: every bucket is touched by the first sample
+                argidx[s] = mi;
+            }
         }
     }
 
@@ -286,56 +297,63 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
         if (new_xyz4) new_xyz4[ob] = make_float4(sx, sy, sz, 0.f);
         if (new_pad) new_pad[ob] = 0;
     }
-    __syncthreads();  // M initialised before any bucket is processed (a bucket is only touched by its own warp,
+    __syncthreads();  // M initialised before any bucket is processed (a bucket is only ever touched by its own warp,
                       // but keep the prologue and the loop cleanly separated)
 
     int par = 0;
     for (int k = 1; k < kn; ++k) {
-        // ---- which of my warp's buckets can change? ------------------------------------------
-        bool act = false;
-        if (owns) {
-            const float dx = fmaxf(fmaxf(lox - sx, sx - hix), 0.f);
-            const float dy = fmaxf(fmaxf(loy - sy, sy - hiy), 0.f);
-            const float dz = fmaxf(fmaxf(loz - sz, sz - hiz), 0.f);
-            const float lb = (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound of every d2
-            act = lb < __uint_as_float(maxbits);
-        }
-        unsigned mask = __ballot_sync(0xffffffffu, act);
-        while (mask) {
-            // up to DEPTH touched buckets of this warp per round: all their loads are issued before the
-            // first one is consumed, so a round costs one L2 round trip
-            int Ls[DEPTH];
-            float4 p[DEPTH][PPL];
-            float m[DEPTH][PPL];
+        // ---- which of my warp's buckets can change?  (d2 >= lb for every point of the box) -------
+        unsigned mask[BPT];
+        unsigned anym = 0u;
 #pragma unroll
-            for (int d = 0; d < DEPTH; ++d) {
-                Ls[d] = -1;
-                if (mask) {
-                    Ls[d] = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int base = (Ls[d] * 32 + warp) * BS + lane;
+        for (int s = 0; s < BPT; ++s) {
+            bool act = false;
+            if (owns[s]) {
+                const float dx = fmaxf(fmaxf(lox[s] - sx, sx - hix[s]), 0.f);
+                const float dy = fmaxf(fmaxf(loy[s] - sy, sy - hiy[s]), 0.f);
+                const float dz = fmaxf(fmaxf(loz[s] - sz, sz - hiz[s]), 0.f);
+                const float lb = (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound of every d2
+                act = lb < __uint_as_float(maxbits[s]);
+            }
+            mask[s] = __ballot_sync(0xffffffffu, act);
+            anym |= mask[s];
+        }
+        while (anym) {
+            // one round: the first touched bucket of every slot; all their loads are issued before the first
+            // one is consumed
+            int Ls[BPT];
+            float4 p[BPT][PPL];
+            float m[BPT][PPL];
+#pragma unroll
+            for (int s = 0; s < BPT; ++s) {
+                Ls[s] = -1;
+                if (mask[s]) {
+                    Ls[s] = __ffs(mask[s]) - 1;
+                    mask[s] &= mask[s] - 1;
+                    const int base = (s * T + Ls[s] * W + warp) * BS + lane;
 #pragma unroll
                     for (int j = 0; j < PPL; ++j) {
-                        p[d][j] = P[base + j * 32];
-                        m[d][j] = M[base + j * 32];
+                        p[s][j] = P[base + j * 32];
+                        m[s][j] = M[base + j * 32];
                     }
                 }
             }
+            anym = 0u;
 #pragma unroll
-            for (int d = 0; d < DEPTH; ++d) {
-                if (Ls[d] < 0) break;  // warp-uniform
-                const int L = Ls[d];
-                const int base = (L * 32 + warp) * BS + lane;
+            for (int s = 0; s < BPT; ++s) {
+                anym |= mask[s];
+                if (Ls[s] < 0) continue;  // warp-uniform
+                const int base = (s * T + Ls[s] * W + warp) * BS + lane;
                 float bestv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
                 unsigned besti = 0xffffffffu;
 #pragma unroll
                 for (int j = 0; j < PPL; ++j) {
-                    const float dd = d2_exact(sx, sy, sz, p[d][j].x, p[d][j].y, p[d][j].z);
-                    const float nm = fminf(m[d][j], dd);
-                    if (nm < m[d][j]) M[base + j * 32] = nm;
-                    const unsigned id = __float_as_uint(p[d][j].w);
+                    const float d = d2_exact(sx, sy, sz, p[s][j].x, p[s][j].y, p[s][j].z);
+                    const float nm = fminf(m[s][j], d);
+                    if (nm < m[s][j]) M[base + j * 32] = nm;
+                    const unsigned id = __float_as_uint(p[s][j].w);
                     if (nm > bestv || (nm == bestv && id < besti)) {
-                        bestv = nm; besti = id; bx = p[d][j].x; by = p[d][j].y; bz = p[d][j].z;
+                        bestv = nm; besti = id; bx = p[s][j].x; by = p[s][j].y; bz = p[s][j].z;
                     }
                 }
                 const unsigned bits = __float_as_uint(bestv);  // bestv >= 0: the bit pattern is order preserving
@@ -345,25 +363,32 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
                 const float wx = __shfl_sync(0xffffffffu, bx, src);
                 const float wy = __shfl_sync(0xffffffffu, by, src);
                 const float wz = __shfl_sync(0xffffffffu, bz, src);
-                if (lane == L) { maxbits = wmax; argidx = wmin; ax = wx; ay = wy; az = wz; }
+                if (lane == Ls[s]) { maxbits[s] = wmax; argidx[s] = wmin; ax[s] = wx; ay[s] = wy; az[s] = wz; }
             }
         }
         // ---- arg-max over all buckets: (value desc, original index asc) -------------------------
-        const unsigned vb = owns ? maxbits : 0u;
+        unsigned vb = 0u, vi = 0xffffffffu;
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+#pragma unroll
+        for (int s = 0; s < BPT; ++s) {
+            if (owns[s] && (maxbits[s] > vb || (maxbits[s] == vb && argidx[s] < vi))) {
+                vb = maxbits[s]; vi = argidx[s]; vx = ax[s]; vy = ay[s]; vz = az[s];
+            }
+        }
         const unsigned wmax = __reduce_max_sync(0xffffffffu, vb);
-        const unsigned wmin = __reduce_min_sync(0xffffffffu, (owns && vb == wmax) ? argidx : 0xffffffffu);
-        const int src = __ffs(__ballot_sync(0xffffffffu, owns && vb == wmax && argidx == wmin)) - 1;
+        const unsigned wmin = __reduce_min_sync(0xffffffffu, vb == wmax ? vi : 0xffffffffu);
+        const int src = __ffs(__ballot_sync(0xffffffffu, vb == wmax && vi == wmin)) - 1;
         if (lane == max(src, 0)) {
-            skey[par][warp] = src < 0 ? 0ull : (((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - wmin));
-            sxyz[par][warp] = make_float4(ax, ay, az, 0.f);
+            skey[par][warp] = wmin == 0xffffffffu ? 0ull : (((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - wmin));
+            sxyz[par][warp] = make_float4(vx, vy, vz, 0.f);
         }
         __syncthreads();
-        const unsigned long long kk = skey[par][lane];
+        const unsigned long long kk = lane < W ? skey[par][lane] : 0ull;
         const unsigned hi = (unsigned)(kk >> 32), lo = (unsigned)kk;
         const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
         const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-        const int slot = __ffs(__ballot_sync(0xffffffffu, hi == mh && lo == ml)) - 1;
-        const float4 w = sxyz[par][slot];
+        const int slot = __ffs(__ballot_sync(0xffffffffu, lane < W && hi == mh && lo == ml)) - 1;
+        const float4 w = sxyz[par][max(slot, 0)];
         sx = w.x; sy = w.y; sz = w.z;
         if (tid == 0) {
             const unsigned sel = 0xffffffffu - ml;
@@ -374,7 +399,7 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
         }
         par ^= 1;
     }
-    for (int k = kn + tid; k < K; k += FG_T) {  // K > len: idx -1, zero rows, padded
+    for (int k = kn + tid; k < K; k += T) {  // K > len: idx -1, zero rows, padded
         if (idx64) idx64[ob + k] = -1;
         if (idx32) idx32[ob + k] = -1;
         if (new_xyz4) new_xyz4[ob + k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -389,10 +414,10 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
     if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
     const int ppl = grid_ppl(N);
     prof_note(N, K);
-#define DPM_FG_CASE(p)                                                                                       \
-    case p:                                                                                                  \
-        fps_grid_kernel<p, (p <= 2 ? 2 : 1)><<<B, FG_T, 0, st>>>(g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, \
-                                                  new_pad, new_len32);                                       \
+#define DPM_FG_ARGS g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, new_pad, new_len32
+#define DPM_FG_CASE(p)                                                \
+    case p:                                                           \
+        fps_grid_kernel<p, 1024, 1><<<B, 1024, 0, st>>>(DPM_FG_ARGS); \
         break;
     switch (ppl) {
         DPM_FG_CASE(1) DPM_FG_CASE(2) DPM_FG_CASE(4) DPM_FG_CASE(8)
