@@ -38,10 +38,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step (reference EXTRACTOR_BATCHSIZE=32)")
     ap.add_argument("--points", type=int, default=65536)
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=0,
                     help="CUDA streams the steps are issued on round-robin (independent frame sequences, like the "
                          "reference's multi-agent mode): the latency-bound FPS chain of one step overlaps the "
-                         "throughput-bound kernels of another")
+                         "throughput-bound kernels of another.  0 = auto: 6, 5 or 4, whichever divides --steps (no "
+                         "partially filled last round inside the timed region), else 4")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -266,7 +267,7 @@ def main():
     dev_pool = [h.to(dev) for h in host_pool]
     pool_mb = nslots * bytes_per_batch / 2 ** 20
 
-    NS = max(1, args.streams)
+    NS = args.streams if args.streams > 0 else next((c for c in (6, 5, 4) if K % c == 0), 4)
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     descbufs = [torch.zeros((F + 1, Cd, S), dtype=torch.float32, device=dev) for _ in range(NS)]
     descbuf = descbufs[0]

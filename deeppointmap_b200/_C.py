@@ -51,6 +51,8 @@ _SIGS = {
     "dpm_ball_query_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_knn_workspace_bytes": ([_i, _i, _i, _i], _sz),
     "dpm_linear_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "dpm_linear_workspace_bytes": ([_i, _i], _sz),
+    "dpm_linear_ws_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp], _i),
     "dpm_layernorm_f32": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
     "dpm_group_ln_relu_max_f32": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "dpm_fp_interp_f32": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),

@@ -109,6 +109,14 @@ int dpm_linear_f32(const float *X, int ldx, const float *W, int ldw, const float
  * network/encoder/utils.py:392-413, and nn.LayerNorm in descriptor_attention.py:21-23.
  * post (M,C) optional (residual identity of InvResMLP, pointnext.py:136; positional
  * embedding of the next attention block, descriptor_attention.py:31,39). */
+/* Same, with a caller workspace of dpm_linear_workspace_bytes(N, K) bytes: the weight matrix is split
+ * once into hi / lo TF32 copies there (one extra launch) and the tensor-core GEMM reads those instead of
+ * splitting W in every CTA -- what the encoder / decoder calls do internally for all their layers. */
+size_t dpm_linear_workspace_bytes(int N, int K);
+int dpm_linear_ws_f32(const float *X, int ldx, const float *W, int ldw, const float *bias,
+                      const float *res, int ldres, float *Y, int ldy, int M, int N, int K, int act,
+                      void *workspace, size_t ws_bytes, dpm_stream_t stream);
+
 int dpm_layernorm_f32(const float *X, int ldx, const float *gamma, const float *beta,
                       const float *post, int ldpost, float *Y, int ldy, int M, int C, int act,
                       dpm_stream_t stream);

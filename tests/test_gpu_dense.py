@@ -46,6 +46,28 @@ def test_linear_strided_weight_columns():
     assert rel_err(Y, X.double() @ Wfull[:, :32].double().T) < TOL
 
 
+@pytest.mark.parametrize("M,N,K,ldw", [(16384, 256, 256, 256), (1000, 64, 32, 35), (16, 2048, 512, 512), (77, 768, 256, 256),
+                                       (300, 3, 64, 64), (4096, 32, 16, 19)])
+def test_linear_presplit_weights(M, N, K, ldw):
+    """dpm_linear_ws_f32: W split once into hi / lo TF32 copies in the caller's workspace (the path every
+    encoder / decoder layer takes); also lifts the 16-byte alignment requirement on W's rows."""
+    g = torch.Generator().manual_seed(M * 7 + N)
+    X = torch.randn(M, K, generator=g).to(DEV)
+    Wfull = torch.randn(N, ldw, generator=g).to(DEV)
+    b, r = torch.randn(N, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    lib = _C.lib()
+    nb = lib.dpm_linear_workspace_bytes(N, K)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    Y = torch.empty(M, N, device=DEV)
+    _C.check(lib.dpm_linear_ws_f32(X.data_ptr(), K, Wfull.data_ptr(), ldw, b.data_ptr(), r.data_ptr(), N, Y.data_ptr(), N,
+                                   M, N, K, _C.ACT_RELU, ws.data_ptr(), nb, _C.stream_ptr()))
+    ref = F.relu(X.double() @ Wfull[:, :K].double().T + b.double() + r.double())
+    assert rel_err(Y, ref) < TOL
+    with pytest.raises(RuntimeError):
+        _C.check(lib.dpm_linear_ws_f32(X.data_ptr(), K, Wfull.data_ptr(), ldw, None, None, N, Y.data_ptr(), N, M, N, K, 0,
+                                       ws.data_ptr(), 16, _C.stream_ptr()))
+
+
 @pytest.mark.parametrize("M,C", [(1, 32), (1000, 32), (77, 128), (16, 2048), (4096, 256), (5, 48)])
 def test_layernorm(M, C):
     g = torch.Generator().manual_seed(C)
