@@ -311,7 +311,8 @@ def main():
         return ev0, ev1
 
     with torch.no_grad():
-        run_steps(W + (1 if NS > 1 else 0), 0, lambda i, q: step(dev_pool[i % nslots], q))  # odd count staggers the streams
+        # every stream is warmed (its workspace allocated) before the timed region; one extra step staggers them
+        run_steps(max(W, NS) + (1 if NS > 1 else 0), 0, lambda i, q: step(dev_pool[i % nslots], q))
         barrier()
         # ---- timed region: K steps, CUDA events on the launching streams ---------------------
         _C.launch_count_reset()

@@ -116,7 +116,7 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                     float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);
 int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
-                    int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st);
+                    int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st, bool pad = false);
 
 // ---- internal launchers shared between translation units ------------------------------
 // xyz4 buffers are float4 (x,y,z,0) rows.

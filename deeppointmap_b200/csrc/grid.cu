@@ -435,6 +435,10 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
 // ---------------------------------------------------------------------------------------
 constexpr int KG_T = 256;
 
+// PAD = false: the reference's hybrid query (slots past the in-radius count repeat slot 0; a query with
+// nothing in the radius falls back to its overall nearest point).  PAD = true: slots past the count are
+// -1 and there is no fallback -- "the K nearest within the radius" (information matrix, pre-filters).
+template <bool PAD>
 __global__ void __launch_bounds__(KG_T)
 knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted, int npad,
                 const int *__restrict__ cell_start, const GridDesc *__restrict__ desc,
@@ -557,7 +561,7 @@ knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted
     const int count = __popc(__ballot_sync(0xffffffffu, ld < INF) & kmask);
     const int kvalid = min(len, K);
     int first = __shfl_sync(0xffffffffu, li, 0);
-    if (count == 0 && len > 0) {
+    if (!PAD && count == 0 && len > 0) {
         // nothing inside the radius: slot 0 of the uncapped kNN is the nearest point overall
         const float4 *pts = p4 + (size_t)b * N;
         unsigned long long best = ~0ull;
@@ -574,7 +578,7 @@ knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted
         }
         first = (int)(unsigned)best;
     }
-    const int oi = lane < count ? li : (lane < kvalid ? first : 0);
+    const int oi = lane < count ? li : (PAD ? -1 : (lane < kvalid ? first : 0));
     if (lane < K) {
         if (idx64) idx64[o + lane] = (int64_t)oi;
         if (idx32) idx32[o + lane] = oi;
@@ -582,14 +586,15 @@ knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted
 }
 
 int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
-                    int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st) {
+                    int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st, bool pad) {
     if (B <= 0 || S <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "knn: bad shape B=%d S=%d N=%d", B, S, N);
     if (K <= 0 || K > 32) return fail(DPM_ERR_UNSUPPORTED, "knn: K=%d not in 1..32", K);
     // keep d2 <= r2  <=>  d2 < nextafter(r2, +inf)
     const float cap = r2 >= 0.f ? __builtin_nextafterf(r2, __builtin_inff()) : 0.f;
     prof_note(S, N);
     dim3 grid((S + KG_T / 32 - 1) / (KG_T / 32), B, 1);
-    knn_grid_kernel<<<grid, KG_T, 0, st>>>(q4, g.sorted, g.npad, g.cell_start, g.desc, p4, S, N, qlen32, K, cap, idx64, idx32);
+    if (pad) knn_grid_kernel<true><<<grid, KG_T, 0, st>>>(q4, g.sorted, g.npad, g.cell_start, g.desc, p4, S, N, qlen32, K, cap, idx64, idx32);
+    else knn_grid_kernel<false><<<grid, KG_T, 0, st>>>(q4, g.sorted, g.npad, g.cell_start, g.desc, p4, S, N, qlen32, K, cap, idx64, idx32);
     DPM_CHECK_LAUNCH("knn", st);
     return DPM_OK;
 }

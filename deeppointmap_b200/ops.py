@@ -135,3 +135,33 @@ def hybrid_query(radius: float, K: int, points: torch.Tensor, centers: torch.Ten
         _C.check(lib.dpm_knn_radius_f32(a.data_ptr(), D1, b.data_ptr(), D2, B, S, N, L2.data_ptr(), K, r2,
                                         idx.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr()), "knn_radius")
     return idx
+
+
+def information_matrix(pointcloud_1: torch.Tensor, pointcloud_2: torch.Tensor, SE3: torch.Tensor, radius: float = 1.0,
+                       return_count: bool = False):
+    """calculate_information_matrix_from_pcd (system/modules/utils.py:60-104, pytorch3d branch) as one native
+    call: (3,N1), (3,N2) CUDA fp32 clouds and a (4,4) pose -> (6,6) information matrix on the same device
+    (no host sync; the reference's caller does `.cpu()` itself).  SURVEY.md section 8f rank 2."""
+    _C.require_cuda(pointcloud_1, pointcloud_2)
+    if pointcloud_1.dim() != 2 or pointcloud_2.dim() != 2 or pointcloud_1.shape[0] != 3 or pointcloud_2.shape[0] != 3:
+        raise ValueError("point clouds must be (3, N)")
+    if tuple(SE3.shape) != (4, 4):
+        raise ValueError("SE3 must be (4, 4)")
+    p1, p2 = _f32c(pointcloud_1), _f32c(pointcloud_2)
+    dev = p1.device
+    T = SE3.to(device=dev, dtype=torch.float32).contiguous()
+    n1, n2 = p1.shape[1], p2.shape[1]
+    info = torch.empty((6, 6), dtype=torch.float32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    if n1 == 0 or n2 == 0:
+        info.zero_()
+        cnt.zero_()
+        return (info, cnt) if return_count else info
+    lib = _C.lib()
+    nb = lib.dpm_information_matrix_workspace_bytes(n1, n2)
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        _C.check(lib.dpm_information_matrix_f32(p1.data_ptr(), n1, p2.data_ptr(), n2, T.data_ptr(), float(radius),
+                                                info.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _C.stream_ptr()), "information_matrix")
+    return (info, cnt) if return_count else info

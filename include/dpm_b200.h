@@ -232,6 +232,16 @@ int dpm_attention_f32(const float *q, int ldq, const float *k, int ldk, const fl
 int dpm_kabsch_f32(const float *src, const float *dst, const float *w, const int32_t *count, int P,
                    int ldk, float *result, uint8_t *inlier, float *conf_out, dpm_stream_t stream);
 
+/* calculate_information_matrix_from_pcd, system/modules/utils.py:60-104 (pytorch3d branch): src (3,N1),
+ * dst (3,N2) channel-first fp32, SE3 16 floats row-major (device memory); every transformed source point
+ * R.p+T is matched to its nearest dst point when d2 <= radius^2; info (36 floats, device) = sum over the
+ * matched dst points of G^T G, G = d(R(w) t + v)/d(w, v).  n_corr (device int32, optional) = matches.
+ * No host sync; SURVEY.md section 8f rank 2. */
+size_t dpm_information_matrix_workspace_bytes(int N1, int N2);
+int dpm_information_matrix_f32(const float *src, int N1, const float *dst, int N2, const float *SE3,
+                               float radius, float *info, int32_t *n_corr, void *workspace,
+                               size_t ws_bytes, dpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,7 @@
 """GPU parity: FPS / kNN / kNN+radius / ball query through the C-ABI vs the C oracle.
 Bar: BIT-EXACT indices (and distances)."""
+import os
+
 import pytest
 import torch
 
@@ -192,3 +194,36 @@ def test_grid_results_are_deterministic():
     for _ in range(3):
         assert torch.equal(ops.sample_farthest_points(pts, K=1024)[1], ref_f)
         assert torch.equal(ops.hybrid_query(0.05, 32, pts, ctr, pad), ref_q)
+
+
+# ---- information matrix: 1-NN within a radius + G^T G reduction ---------------
+@pytest.mark.parametrize("n1,n2", [(16384, 16384), (65536, 60000), (1500, 900), (5000, 100), (1, 1)])
+def test_information_matrix_vs_oracle(n1, n2):
+    """tolerance 1e-4 relative to the largest entry (fp32 sums of ~1e4 products in the reference)"""
+    import math
+    from oracle import infomat_ref
+    from deeppointmap_b200 import ops
+    c0 = data.kitti_shape_cloud(21, n1) * 60.0
+    c1, _, _ = data.rigid_move(c0 / 60.0, yaw_deg=2.0, t_m=(1.0, 0.1, 0.0), jitter_m=0.02, seed=22)
+    c1 = (c1 * 60.0)[:, torch.randperm(n1, generator=torch.Generator().manual_seed(3))[:n2] % n1].contiguous()
+    a = math.radians(2.0)
+    T = torch.eye(4)
+    T[0, 0], T[0, 1], T[1, 0], T[1, 1] = math.cos(a), -math.sin(a), math.sin(a), math.cos(a)
+    T[:3, 3] = torch.tensor([1.0, 0.1, 0.0])
+    want, n = infomat_ref.information_matrix(c0, c1, T, 1.0)
+    got, cnt = ops.information_matrix(c0.to(DEV), c1.to(DEV), T, 1.0, return_count=True)
+    assert abs(int(cnt) - n) <= max(2, n // 2000)  # a transformed coordinate may differ by 1 ulp from torch's matmul
+    assert float((got.cpu() - want).abs().max()) <= 1e-4 * max(float(want.abs().max()), 1.0)
+
+
+def test_information_matrix_golden_and_empty():
+    import numpy as np
+    from conftest import GOLDEN
+    from deeppointmap_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "infomat.npz"))
+    for name in ("kitti6k", "uniform", "far_apart"):
+        got = ops.information_matrix(torch.from_numpy(g[name + "_p1"]).to(DEV), torch.from_numpy(g[name + "_p2"]).to(DEV),
+                                     torch.from_numpy(g[name + "_T"]), float(g[name + "_radius"])).cpu()
+        want = torch.from_numpy(g[name + "_info"])
+        assert float((got - want).abs().max()) <= 1e-4 * max(float(want.abs().max()), 1e-30), name
+    assert float(ops.information_matrix(torch.zeros(3, 0, device=DEV), torch.zeros(3, 5, device=DEV), torch.eye(4)).abs().max()) == 0.0

@@ -203,3 +203,31 @@ def test_oracle_reproduces_golden_synthetic(cfg, checkpoint, golden_synth):
                                               torch.from_numpy(g["desc_moved"]), 0.5)
     assert np.abs(R.numpy() - g["R"]).max() < 1e-6 and np.abs(T.numpy() - g["T"]).max() < 1e-5
     assert len(conf) == len(g["conf"])
+
+
+# ---- information matrix -----------------------------------------------------
+@needs_ref
+@pytest.mark.reference
+def test_information_matrix_matches_reference():
+    """oracle/infomat_ref.py vs the reference function itself (CPU knn_points stand-in for pytorch3d)."""
+    from oracle import infomat_ref
+    from ref_infomat import cases, reference_information_matrix
+    for name, (p1, p2, T, radius) in cases().items():
+        want = reference_information_matrix(p1, p2, T, radius)
+        got, n = infomat_ref.information_matrix(p1, p2, T, radius)
+        assert got.shape == (6, 6)
+        if name == "far_apart":
+            assert n == 0 and float(want.abs().max()) == 0.0 and float(got.abs().max()) == 0.0
+        else:
+            assert n > 100
+            assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()), name
+
+
+def test_information_matrix_oracle_matches_golden():
+    from oracle import infomat_ref
+    g = np.load(os.path.join(ROOT, "tests", "golden", "infomat.npz"))
+    for name in ("kitti6k", "uniform", "far_apart"):
+        got, _ = infomat_ref.information_matrix(torch.from_numpy(g[name + "_p1"]), torch.from_numpy(g[name + "_p2"]),
+                                                torch.from_numpy(g[name + "_T"]), float(g[name + "_radius"]))
+        want = torch.from_numpy(g[name + "_info"])
+        assert float((got - want).abs().max()) <= 1e-5 * max(float(want.abs().max()), 1e-30), name
