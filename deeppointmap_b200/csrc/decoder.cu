@@ -989,17 +989,15 @@ static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float
         // self attention (shared weights for src and dst), add & norm1, then "+ pos" again
         DPM_TRY(linear_launch(x, C, L.sa_in_w, C, L.sa_in_b, nullptr, 0, qkv, 3 * C, R, 3 * C, C, DPM_ACT_NONE, st));
         DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 0, H, st));
-        DPM_TRY(linear_launch(att, C, L.sa_out_w, C, L.sa_out_b, x, C, y, C, R, C, C, DPM_ACT_NONE, st));
-        DPM_TRY(layernorm_launch(y, C, L.n1_w, L.n1_b, pos, C, x, C, R, C, DPM_ACT_NONE, st));
+        DPM_TRY(linear_ln_launch(att, C, L.sa_out_w, C, L.sa_out_b, x, C, L.n1_w, L.n1_b, pos, C, y, x, C, R, C, C, DPM_ACT_NONE, st));
         // cross attention both ways, add & norm2
         DPM_TRY(linear_launch(x, C, L.ca_in_w, C, L.ca_in_b, nullptr, 0, qkv, 3 * C, R, 3 * C, C, DPM_ACT_NONE, st));
         DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 1, H, st));
-        DPM_TRY(linear_launch(att, C, L.ca_out_w, C, L.ca_out_b, x, C, y, C, R, C, C, DPM_ACT_NONE, st));
-        DPM_TRY(layernorm_launch(y, C, L.n2_w, L.n2_b, nullptr, 0, x, C, R, C, DPM_ACT_NONE, st));
+        DPM_TRY(linear_ln_launch(att, C, L.ca_out_w, C, L.ca_out_b, x, C, L.n2_w, L.n2_b, nullptr, 0, y, x, C, R, C, C, DPM_ACT_NONE, st));
         // mlp, add & norm3 (+ pos for the next layer)
         DPM_TRY(linear_launch(x, C, L.m0_w, C, L.m0_b, nullptr, 0, att, C, R, C, C, DPM_ACT_RELU, st));
-        DPM_TRY(linear_launch(att, C, L.m2_w, C, L.m2_b, x, C, y, C, R, C, C, DPM_ACT_NONE, st));
-        DPM_TRY(layernorm_launch(y, C, L.n3_w, L.n3_b, last ? nullptr : pos, C, x, C, R, C, DPM_ACT_NONE, st));
+        DPM_TRY(linear_ln_launch(att, C, L.m2_w, C, L.m2_b, x, C, L.n3_w, L.n3_b, last ? nullptr : pos, C, y, x, C, R, C, C,
+                                 DPM_ACT_NONE, st));
     }
     return DPM_OK;
 }

@@ -364,6 +364,16 @@ int group_from_xyz_launch(const float *Wsa, int ldw, const float *bias, const fl
     return DPM_OK;
 }
 
+int linear_ln_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res, int ldres,
+                     const float *gamma, const float *beta, const float *post, int ldpost, float *tmp, float *Y, int ldy,
+                     int M, int N, int K, int act, cudaStream_t st) {
+    int rc = DPM_OK;
+    if (linear_ln_tc_launch(X, ldx, W, ldw, bias, res, ldres, gamma, beta, post, ldpost, Y, ldy, M, N, K, act, st, &rc))
+        return rc;
+    DPM_TRY(linear_launch(X, ldx, W, ldw, bias, res, ldres, tmp, N, M, N, K, DPM_ACT_NONE, st));
+    return layernorm_launch(tmp, N, gamma, beta, post, ldpost, Y, ldy, M, N, act, st);
+}
+
 int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *Wxyz,
                  int ldw, const float *gamma, const float *beta, float radius, float *out, int B, int N, int S,
                  int K, int Cout, cudaStream_t st) {

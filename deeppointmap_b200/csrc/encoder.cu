@@ -286,10 +286,12 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
                 DPM_TRY(linear_launch(dst.fea, Cout, Wla, Cout + 3, bla, nullptr, 0, Z2, Cout, B * S, Cout, Cout,
                                       DPM_ACT_NONE, st));
                 DPM_TRY(group_launch(Z2, dst.xyz, dst.xyz, g2, Wla + Cout, Cout + 3, gla, bela, (float)r, la, B, S, S, K, Cout, st));
-                DPM_TRY(linear_launch(la, Cout, W1, Cout, b1, nullptr, 0, h1, Ch, B * S, Ch, Cout, DPM_ACT_NONE, st));
-                DPM_TRY(layernorm_launch(h1, Ch, g1, be1, nullptr, 0, h1, Ch, B * S, Ch, DPM_ACT_RELU, st));
-                DPM_TRY(linear_launch(h1, Ch, W2, Ch, b2, nullptr, 0, h2, Cout, B * S, Cout, Ch, DPM_ACT_NONE, st));
-                DPM_TRY(layernorm_launch(h2, Cout, g2w, be2, dst.fea, Cout, nf, Cout, B * S, Cout, DPM_ACT_RELU, st));
+                // Conv1d - LN - ReLU - Conv1d - LN - (+identity) - ReLU; the LayerNorm rides in the GEMM epilogue when
+                // the row fits one column tile (<= 256 channels)
+                DPM_TRY(linear_ln_launch(la, Cout, W1, Cout, b1, nullptr, 0, g1, be1, nullptr, 0, h1, h1, Ch, B * S, Ch, Cout,
+                                         DPM_ACT_RELU, st));
+                DPM_TRY(linear_ln_launch(h1, Ch, W2, Ch, b2, nullptr, 0, g2w, be2, dst.fea, Cout, h2, nf, Cout, B * S, Cout, Ch,
+                                         DPM_ACT_RELU, st));
             }
             knn_off += (size_t)B * S * K;
             dst.fea = nf;
@@ -318,10 +320,10 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
         if (!dry) {
             set_unit_rows(l1.n);
             DPM_TRY(fp_interp_launch(l1.xyz, l2.xyz, l1.fea, l2.fea, l2.pad, cat, B, l1.n, l2.n, l1.c, l2.c, st));
-            DPM_TRY(linear_launch(cat, Ccat, W1, Ccat, b1, nullptr, 0, h1, up_out, B * l1.n, up_out, Ccat, DPM_ACT_NONE, st));
-            DPM_TRY(layernorm_launch(h1, up_out, g1, be1, nullptr, 0, h1, up_out, B * l1.n, up_out, DPM_ACT_RELU, st));
-            DPM_TRY(linear_launch(h1, up_out, W2, up_out, b2, nullptr, 0, h2, up_out, B * l1.n, up_out, up_out, DPM_ACT_NONE, st));
-            DPM_TRY(layernorm_launch(h2, up_out, g2, be2, nullptr, 0, h2, up_out, B * l1.n, up_out, DPM_ACT_RELU, st));
+            DPM_TRY(linear_ln_launch(cat, Ccat, W1, Ccat, b1, nullptr, 0, g1, be1, nullptr, 0, h1, h1, up_out, B * l1.n, up_out,
+                                     Ccat, DPM_ACT_RELU, st));
+            DPM_TRY(linear_ln_launch(h1, up_out, W2, up_out, b2, nullptr, 0, g2, be2, nullptr, 0, h2, h2, up_out, B * l1.n, up_out,
+                                     up_out, DPM_ACT_RELU, st));
         }
         Level &nu = lv[nl++];
         nu = l1;

@@ -168,11 +168,17 @@ __device__ __forceinline__ void produce_tile_presplit(const float *__restrict__ 
     }
 }
 
-template <int BN, int STAGES, bool PRESPLIT>
+struct LnArgs {  // fused LayerNorm epilogue: Y = act(LN_N(acc + bias + res) * gamma + beta + post)
+    const float *gamma, *beta, *post;
+    int ldpost;
+};
+
+template <int BN, int STAGES, bool PRESPLIT, bool LN>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W, int ldw,
-                 const float *__restrict__ bias, const float *__restrict__ res, int ldres, float *__restrict__ Y,
-                 int ldy, int M, int N, int K, int act, long long sX, long long sW, long long sY, long long wlo_off) {
+                 const float *__restrict__ bias, const float *res, int ldres, float *Y,
+                 int ldy, int M, int N, int K, int act, long long sX, long long sW, long long sY, long long wlo_off,
+                 LnArgs ln) {
     X += (size_t)blockIdx.z * sX;
     W += (size_t)blockIdx.z * sW;
     Y += (size_t)blockIdx.z * sY;
@@ -238,6 +244,116 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
         const bool vec = ((ldy & 3) == 0) && ((((uintptr_t)Y) & 15) == 0) && (!bias || ((((uintptr_t)bias) & 15) == 0)) &&
                          (!res || (((ldres & 3) == 0) && ((((uintptr_t)res) & 15) == 0)));
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // this lane's (row within a group of 4, column) when storing
+        if (LN) {
+            // The whole row lives in this CTA (N <= BN, one column tile).  The 128 x N tile of acc + bias + res is
+            // parked in shared memory (row stride BN + 4), the two warps that share a TMEM lane quarter (one per
+            // column half) exchange their partial row sums through shared memory, and the normalised rows leave
+            // as whole 128-byte segments.  Two-pass variance, like the stand-alone LayerNorm kernel.
+            constexpr int TS = BN + 4;
+            float *tile = reinterpret_cast<float *>(smem);
+            float *stat = tile + 128 * TS;  // [2 passes][2 halves][128 rows]
+            const int cbeg = grp * CHALF, cend = (BN >= 64 ? (grp + 1) * CHALF : (grp == 0 ? BN : 0));
+            float sum[8], mean[8], rstd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+#pragma unroll 1
+            for (int cb = cbeg; cb < cend; cb += 32) {
+                if (cb >= N) break;  // warp-uniform
+                float v[32], vc[32];
+                tmem_ld32(tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)cb, v);
+                tmem_ld32(tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)(BN + cb), vc);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4 *>(tile + (quarter * 32 + lane) * TS + cb + 4 * q) =
+                        make_float4(v[4 * q] + vc[4 * q], v[4 * q + 1] + vc[4 * q + 1], v[4 * q + 2] + vc[4 * q + 2],
+                                    v[4 * q + 3] + vc[4 * q + 3]);
+                __syncwarp();
+                const int col = cb + c4;
+                const bool cok = col < N;  // N % 4 == 0
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias && cok) bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int lr = quarter * 32 + i * 4 + rsub, row = m0 + lr;
+                    float4 o = *reinterpret_cast<const float4 *>(tile + lr * TS + col);
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (res && cok && row < M) r4 = *reinterpret_cast<const float4 *>(res + (size_t)row * ldres + col);
+                    o.x += bb.x + r4.x; o.y += bb.y + r4.y; o.z += bb.z + r4.z; o.w += bb.w + r4.w;
+                    if (!cok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(tile + lr * TS + col) = o;
+                    sum[i] += (o.x + o.y) + (o.z + o.w);
+                }
+            }
+            // ---- mean ----
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+                sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+                sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 4);
+                if ((lane & 7) == 0) stat[grp * 128 + quarter * 32 + i * 4 + rsub] = sum[i];
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // the two warps of this lane quarter
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int lr = quarter * 32 + i * 4 + rsub;
+                mean[i] = (stat[lr] + stat[128 + lr]) / (float)N;
+                sum[i] = 0.f;
+            }
+            // ---- variance ----
+#pragma unroll 1
+            for (int cb = cbeg; cb < cend; cb += 32) {
+                if (cb >= N) break;
+                const int col = cb + c4;
+                if (col < N) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 o = *reinterpret_cast<const float4 *>(tile + (quarter * 32 + i * 4 + rsub) * TS + col);
+                        const float dx = o.x - mean[i], dy = o.y - mean[i], dz = o.z - mean[i], dw = o.w - mean[i];
+                        sum[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+                sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+                sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 4);
+                if ((lane & 7) == 0) stat[256 + grp * 128 + quarter * 32 + i * 4 + rsub] = sum[i];
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int lr = quarter * 32 + i * 4 + rsub;
+                rstd[i] = 1.0f / sqrtf((stat[256 + lr] + stat[384 + lr]) / (float)N + 1e-5f);
+            }
+            // ---- normalise, affine, post-add, activation, store ----
+#pragma unroll 1
+            for (int cb = cbeg; cb < cend; cb += 32) {
+                if (cb >= N) break;
+                const int col = cb + c4;
+                if (col >= N) continue;
+                const float4 g4 = __ldg(reinterpret_cast<const float4 *>(ln.gamma + col));
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(ln.beta + col));
+                float4 p4[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = m0 + quarter * 32 + i * 4 + rsub;
+                    p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ln.post && row < M) p4[i] = *reinterpret_cast<const float4 *>(ln.post + (size_t)row * ln.ldpost + col);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int lr = quarter * 32 + i * 4 + rsub, row = m0 + lr;
+                    float4 o = *reinterpret_cast<const float4 *>(tile + lr * TS + col);
+                    o.x = (o.x - mean[i]) * rstd[i] * g4.x + b4.x + p4[i].x;
+                    o.y = (o.y - mean[i]) * rstd[i] * g4.y + b4.y + p4[i].y;
+                    o.z = (o.z - mean[i]) * rstd[i] * g4.z + b4.z + p4[i].z;
+                    o.w = (o.w - mean[i]) * rstd[i] * g4.w + b4.w + p4[i].w;
+                    if (act == DPM_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (row < M) *reinterpret_cast<float4 *>(Y + (size_t)row * ldy + col) = o;
+                }
+            }
+        } else
 #pragma unroll 1
         for (int cb = grp * CHALF; cb < (BN >= 64 ? (grp + 1) * CHALF : (grp == 0 ? BN : 0)); cb += 32) {
             if (n0 + cb >= N) break;  // warp-uniform
@@ -313,11 +429,11 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
     }
 }
 
-template <int BN, int STAGES, bool PRESPLIT>
+template <int BN, int STAGES, bool PRESPLIT, bool LN = false>
 static int launch_t(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
                     const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
-                    int act, long long wlo_off, cudaStream_t st) {
-    auto kern = linear_tc_kernel<BN, STAGES, PRESPLIT>;
+                    int act, long long wlo_off, cudaStream_t st, LnArgs ln = LnArgs{nullptr, nullptr, nullptr, 0}) {
+    auto kern = linear_tc_kernel<BN, STAGES, PRESPLIT, LN>;
     const size_t smem = (size_t)STAGES * (2 * A_TILE + 2 * BN * 128) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
@@ -325,12 +441,39 @@ static int launch_t(const float *X, int ldx, long long sX, const float *W, int l
         configured = true;
     }
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch);
-    kern<<<grid, THREADS, smem, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY, wlo_off);
-    DPM_CHECK_LAUNCH("linear_tc", st);
+    kern<<<grid, THREADS, smem, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY, wlo_off, ln);
+    DPM_CHECK_LAUNCH(LN ? "linear_ln_tc" : "linear_tc", st);
     return DPM_OK;
 }
 
 }  // namespace tc
+
+// Y = act(LayerNorm_N(X W^T + bias + res) * gamma + beta + post) in ONE launch when the row fits one column
+// tile (N <= 256) and the weights were pre-split for this call; false = not eligible (caller runs the two
+// kernels).  Y may alias res and / or post (a CTA reads its own rows before it writes them).
+bool linear_ln_tc_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res,
+                         int ldres, const float *gamma, const float *beta, const float *post, int ldpost, float *Y,
+                         int ldy, int M, int N, int K, int act, cudaStream_t st, int *rc) {
+    static const bool off = getenv("DPM_NO_LN_FUSION") != nullptr;
+    if (off || N > 256 || (N & 3) || M < 1 || (K & 3) || (ldx & 3) || (((uintptr_t)X) & 15)) return false;
+    if ((ldy & 3) || (((uintptr_t)Y) & 15) || (bias && (((uintptr_t)bias) & 15)) || (((uintptr_t)gamma) & 15) ||
+        (((uintptr_t)beta) & 15))
+        return false;
+    if (res && ((ldres & 3) || (((uintptr_t)res) & 15))) return false;
+    if (post && ((ldpost & 3) || (((uintptr_t)post) & 15))) return false;
+    const float *Ws = split_lookup(W, N, K, ldw);
+    if (!Ws || getenv("DPM_NO_TC")) return false;
+    prof_note((long long)M, (long long)N * K);
+    const tc::LnArgs ln{gamma, beta, post, ldpost};
+    const long long lo = (long long)N * K;
+#define DPM_TC_ARGS X, ldx, 0, Ws, K, 0, bias, res, ldres, Y, ldy, 0, M, N, K, 1, act, lo, st, ln
+    if (N <= 32) *rc = tc::launch_t<32, 4, true, true>(DPM_TC_ARGS);
+    else if (N <= 64) *rc = tc::launch_t<64, 4, true, true>(DPM_TC_ARGS);
+    else if (N <= 128) *rc = tc::launch_t<128, 3, true, true>(DPM_TC_ARGS);
+    else *rc = tc::launch_t<256, 2, true, true>(DPM_TC_ARGS);
+#undef DPM_TC_ARGS
+    return true;
+}
 
 bool linear_tc_eligible(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, int M, int N, int K) {
     static const bool off = getenv("DPM_NO_TC") != nullptr;
