@@ -1,0 +1,119 @@
+"""Frame-to-frame odometry over a synthetic sequence (BASELINE.json config 5).
+
+The reference's `pipeline/infer.py` cannot start on this image and its tree does not
+exist on the GPU box, so this is the part of its odometry loop that IS the hot path -- what
+`ExtractionThread.process` + `OdometryThread` do per scan (system/modules/odometry.py:36-54, 96-121):
+encode scans in batches of `EXTRACTOR_BATCHSIZE`, register every scan against its predecessor, chain the
+relative poses -- with the descriptors kept on the device instead of `.cpu()` / `.to(device)` round trips.
+
+`corridor_world` / `corridor_frames` build a deterministic KITTI-shaped world (ground strip + facades along a
+road) and what a 60 m sensor moving along a smooth trajectory sees of it, so the estimated trajectory can be
+checked against ground truth.
+"""
+import math
+from typing import List, Tuple
+
+import torch
+
+
+def corridor_world(seed: int, length_m: float, half_width_m: float = 70.0, ground_density: float = 7.0,
+                   facades_per_100m: int = 24, device="cpu") -> torch.Tensor:
+    """(3, P) fp32 world points in metres: a ground strip along +x and vertical facades on both sides."""
+    g = torch.Generator().manual_seed(int(seed))
+    L = float(length_m) + 140.0
+    ng = int(L * 2 * half_width_m * ground_density)
+    ground = torch.stack([torch.rand(ng, generator=g) * L - 70.0, (torch.rand(ng, generator=g) * 2 - 1) * half_width_m,
+                          -1.73 + 0.02 * torch.randn(ng, generator=g)])
+    nf = max(1, int(L / 100.0 * facades_per_100m))
+    cx = torch.rand(nf, generator=g) * L - 70.0
+    cy = (torch.rand(nf, generator=g) * 2 - 1) * (half_width_m - 8.0)
+    cy = torch.where(cy.abs() < 6.0, cy.sign() * 6.0 + cy, cy)  # keep the road itself free
+    heading = torch.rand(nf, generator=g) * math.pi
+    length = 5.0 + 20.0 * torch.rand(nf, generator=g)
+    per = 2500
+    pid = torch.arange(nf).repeat_interleave(per)
+    along = (torch.rand(nf * per, generator=g) - 0.5) * length[pid]
+    facade = torch.stack([cx[pid] + along * torch.cos(heading[pid]), cy[pid] + along * torch.sin(heading[pid]),
+                          -1.73 + 6.0 * torch.rand(nf * per, generator=g)])
+    return torch.cat([ground, facade], dim=1).to(device=device, dtype=torch.float32).contiguous()
+
+
+def trajectory(n_frames: int, step_m: float = 1.0, max_yaw_deg: float = 2.0) -> torch.Tensor:
+    """(n,4,4) fp64 sensor poses in the world: `step_m` per frame along a gently weaving heading."""
+    poses, x, y, yaw = [], 0.0, 0.0, 0.0
+    for i in range(n_frames):
+        T = torch.eye(4, dtype=torch.float64)
+        c, s = math.cos(yaw), math.sin(yaw)
+        T[0, 0], T[0, 1], T[1, 0], T[1, 1] = c, -s, s, c
+        T[0, 3], T[1, 3] = x, y
+        poses.append(T)
+        yaw_rate = math.radians(max_yaw_deg) * math.sin(2 * math.pi * i / 97.0) * math.cos(2 * math.pi * i / 41.0)
+        yaw = max(-0.35, min(0.35, yaw + yaw_rate))
+        x += step_m * math.cos(yaw)
+        y += step_m * math.sin(yaw)
+    return torch.stack(poses)
+
+
+@torch.no_grad()
+def corridor_frames(world: torch.Tensor, poses: torch.Tensor, n_points: int, seed: int = 0, max_range_m: float = 60.0,
+                    jitter_m: float = 0.01, scale: float = 60.0) -> torch.Tensor:
+    """What the sensor sees: (F, 3, n_points) fp32 normalised clouds in the sensor frames (1 m <= |p| <= range,
+    a fresh random subset and jitter per frame) on the world tensor's device."""
+    dev = world.device
+    g = torch.Generator(device=dev).manual_seed(int(seed))
+    out = torch.empty((poses.shape[0], 3, n_points), dtype=torch.float32, device=dev)
+    for i in range(poses.shape[0]):
+        Tinv = torch.linalg.inv(poses[i]).to(device=dev, dtype=torch.float32)
+        near = ((world[0] - float(poses[i, 0, 3])).abs() <= max_range_m)
+        p = Tinv[:3, :3] @ world[:, near] + Tinv[:3, 3:]
+        d = p.norm(dim=0)
+        p = p[:, (d >= 1.0) & (d <= max_range_m)]
+        if p.shape[1] < n_points:
+            raise ValueError(f"frame {i}: only {p.shape[1]} world points in range, need {n_points} (raise ground_density)")
+        sel = torch.randperm(p.shape[1], generator=g, device=dev)[:n_points]
+        out[i] = (p[:, sel] + jitter_m * torch.randn((3, n_points), generator=g, device=dev)) / scale
+    return out
+
+
+@torch.no_grad()
+def run_odometry(encoder, decoder, frames: torch.Tensor, batch: int = 32, coor_scale: float = 60.0,
+                 num_sample: float = 0.5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frames (F,3,N) on the device -> (relative (F-1,16) pose records [R(9) T(3) rmse ...] of scan i-1 -> scan i,
+    absolute (F,4,4) fp64 poses chained from identity).  One encoder call and one registration call per batch,
+    descriptors stay on the device, one host read at the end."""
+    F = frames.shape[0]
+    S, Cd = encoder._out_points, encoder.final_channel + 3
+    desc = torch.zeros((batch + 1, Cd, S), dtype=torch.float32, device=frames.device)
+    records: List[torch.Tensor] = []
+    have_prev = False
+    for b0 in range(0, F, batch):
+        nb = min(batch, F - b0)
+        encoder.descriptors(frames[b0:b0 + nb], None, coor_scale=coor_scale, out=desc[1:nb + 1])
+        lo = 0 if have_prev else 1  # the first scan of the sequence has no predecessor
+        if nb + 1 - lo >= 2:
+            res, _ = decoder.registration_forward_batch(desc[lo:nb], desc[lo + 1:nb + 1], num_sample)
+            records.append(res)
+        desc[0].copy_(desc[nb])
+        have_prev = True
+    rel = torch.cat(records) if records else torch.zeros((0, 16), device=frames.device)
+    host = rel.double().cpu()
+    poses = [torch.eye(4, dtype=torch.float64)]
+    for i in range(host.shape[0]):
+        T = torch.eye(4, dtype=torch.float64)
+        T[:3, :3] = host[i, 0:9].view(3, 3)
+        T[:3, 3] = host[i, 9:12]
+        poses.append(poses[-1] @ torch.linalg.inv(T))  # p_i = T p_{i-1}  =>  pose_i = pose_{i-1} T^-1
+    return rel, torch.stack(poses)
+
+
+def relative_errors(rel: torch.Tensor, gt_poses: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """per-pair translation error (m) and rotation error (deg) of the estimated scan i-1 -> i transforms"""
+    host = rel.double().cpu()
+    te, re = [], []
+    for i in range(host.shape[0]):
+        gt = torch.linalg.inv(gt_poses[i + 1]) @ gt_poses[i]
+        R, t = host[i, 0:9].view(3, 3), host[i, 9:12]
+        te.append(float((t - gt[:3, 3]).norm()))
+        c = float(((R.T @ gt[:3, :3]).trace() - 1) / 2)
+        re.append(math.degrees(math.acos(max(-1.0, min(1.0, c)))))
+    return torch.tensor(te), torch.tensor(re)
