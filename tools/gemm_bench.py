@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Micro-benchmark of the tensor-core linear (dpm_linear_ws_f32) on the decoder / encoder shapes.
 Round-1 findings (B200): ~19 us of every call is size-independent (split launch + one 128-row tile's
-prologue, 8 K blocks at ~1 us each through 2 stages, TMEM round trip); the epilogue adds ~6 us."""
+prologue, 8 K blocks at ~1.2 us each through 2 stages, TMEM round trip); the epilogue adds ~6 us.  A K block
+costs max(W stage fill ~1 us, 12 tf32 MMAs ~0.8 us): with hi + lo copies a 128 x 256 tile leaves room for two stages
+only, so neither hides behind the other; prefetching the X tile into registers one block ahead changes nothing."""
 import os
 import subprocess
 import sys
