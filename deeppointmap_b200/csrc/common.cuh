@@ -60,6 +60,7 @@ struct Arena {
 };
 
 int device_sm_count();
+int current_device();
 
 // ---- device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__

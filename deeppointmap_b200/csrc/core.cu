@@ -72,6 +72,12 @@ static void prof_record(const char *tag, cudaStream_t st) {
     ++g_prof_n;
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    return dev;
+}
+
 int device_sm_count() {
     static thread_local int cached = 0;
     if (cached == 0) {

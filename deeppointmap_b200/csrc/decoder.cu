@@ -376,10 +376,11 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
     if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
     const size_t smem = 2 * (size_t)ATT_KC * 32 * sizeof(float);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
+    const unsigned long long devbit = 1ull << (current_device() & 63);
+    if (!(configured & devbit)) {
         DPM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= devbit;
     }
     static const bool simt = getenv("DPM_ATT_SIMT") != nullptr;  // developer A/B switch
     if (!simt) {
@@ -1057,11 +1058,12 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     int kp2 = 2;
     while (kp2 < k) kp2 <<= 1;
     const size_t tk_smem = (size_t)kp2 * 8 + 32 * 256 * 4;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
+    const unsigned long long devbit = 1ull << (current_device() & 63);
+    if (!(configured & devbit)) {
         DPM_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(TOPK_MAXK * 8 + 32 * 256 * 4)));
-        configured = true;
+        configured |= devbit;
     }
     topk_kernel<<<P, TOPK_T, tk_smem, st>>>(S, M * N, N, k, kp2, si, di, conf);
     DPM_CHECK_LAUNCH("topk", st);

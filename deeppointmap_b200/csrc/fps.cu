@@ -172,11 +172,12 @@ static int fps_launch_t(const float4 *xyz4, int B, int N, const int *len32, int 
                         int32_t *idx32, float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
     auto kern = fps_kernel<P, CS>;
     const size_t smem = (size_t)P * FPS_T * sizeof(float4);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
+    const unsigned long long devbit = 1ull << (current_device() & 63);
+    if (!(configured & devbit)) {
         DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (CS > 8) DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        configured = true;
+        configured |= devbit;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS, B, 1);

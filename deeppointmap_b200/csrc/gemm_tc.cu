@@ -435,10 +435,11 @@ static int launch_t(const float *X, int ldx, long long sX, const float *W, int l
                     int act, long long wlo_off, cudaStream_t st, LnArgs ln = LnArgs{nullptr, nullptr, nullptr, 0}) {
     auto kern = linear_tc_kernel<BN, STAGES, PRESPLIT, LN>;
     const size_t smem = (size_t)STAGES * (2 * A_TILE + 2 * BN * 128) + 1024;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
+    const unsigned long long devbit = 1ull << (current_device() & 63);
+    if (!(configured & devbit)) {
         DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= devbit;
     }
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch);
     kern<<<grid, THREADS, smem, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY, wlo_off, ln);

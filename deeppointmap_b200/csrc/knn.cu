@@ -201,10 +201,11 @@ static int knn_launch_t(const float4 *q4, const float4 *p4, int B, int S, int N,
                         float *d2out, cudaStream_t st) {
     auto kern = knn_kernel<QW>;
     const size_t smem = 2 * (size_t)KNN_TILE * sizeof(float4);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
+    const unsigned long long devbit = 1ull << (current_device() & 63);
+    if (!(configured & devbit)) {
         DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured |= devbit;
     }
     dim3 grid((S + KNN_WARPS * QW - 1) / (KNN_WARPS * QW), B, 1);
     kern<<<grid, KNN_T, smem, st>>>(q4, p4, S, N, qlen32, plen32, K, cap, mode, idx64, idx32, d2out);
