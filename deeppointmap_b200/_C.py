@@ -53,6 +53,8 @@ _SIGS = {
     "dpm_linear_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "dpm_linear_workspace_bytes": ([_i, _i], _sz),
     "dpm_linear_ws_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp], _i),
+    "dpm_linear_ln_workspace_bytes": ([_i, _i, _i], _sz),
+    "dpm_linear_ln_ws_f32": ([_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp], _i),
     "dpm_layernorm_f32": ([_vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp], _i),
     "dpm_group_ln_relu_max_f32": ([_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "dpm_fp_interp_f32": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
@@ -71,6 +73,8 @@ _SIGS = {
     "dpm_attention_f32": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp], _i),
     "dpm_information_matrix_workspace_bytes": ([_i, _i], _sz),
     "dpm_information_matrix_f32": ([_vp, _i, _vp, _i, _vp, _f, _vp, _vp, _vp, _sz, _vp], _i),
+    "dpm_frontend_workspace_bytes": ([_ll], _sz),
+    "dpm_frontend_f32": ([_vp, _i, _i, _f, _f, _f, _f, _ll, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_kabsch_f32": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
 

@@ -507,6 +507,32 @@ extern "C" int dpm_linear_ws_f32(const float *X, int ldx, const float *W, int ld
     return rc;
 }
 
+extern "C" size_t dpm_linear_ln_workspace_bytes(int M, int N, int K) {
+    Arena a(nullptr, 0);
+    a.get<float>((size_t)2 * (N > 0 ? N : 0) * (K > 0 ? K : 0));
+    a.get<float>((size_t)(M > 0 ? M : 0) * (N > 0 ? N : 0));
+    return a.off + 256;
+}
+
+extern "C" int dpm_linear_ln_ws_f32(const float *X, int ldx, const float *W, int ldw, const float *bias,
+                                    const float *res, int ldres, const float *gamma, const float *beta,
+                                    const float *post, int ldpost, float *Y, int ldy, int M, int N, int K, int act,
+                                    void *ws, size_t ws_bytes, dpm_stream_t stream) {
+    if (!X || !W || !Y || !gamma || !beta || !ws) return fail(DPM_ERR_ARG, "linear_ln: null pointer");
+    if (M <= 0 || N <= 0 || K <= 0) return fail(DPM_ERR_SHAPE, "linear_ln: bad shape M=%d N=%d K=%d", M, N, K);
+    if (ws_bytes < dpm_linear_ln_workspace_bytes(M, N, K)) return fail(DPM_ERR_WORKSPACE, "linear_ln: workspace too small");
+    set_unit_rows(0);
+    Arena a(ws, ws_bytes);
+    split_begin();
+    split_add(a, W, N, K, ldw);
+    float *tmp = a.get<float>((size_t)M * N);
+    DPM_TRY(split_run((cudaStream_t)stream));
+    const int rc = linear_ln_launch(X, ldx, W, ldw, bias, res, ldres, gamma, beta, post, ldpost, tmp, Y, ldy, M, N, K, act,
+                                    (cudaStream_t)stream);
+    split_begin();
+    return rc;
+}
+
 extern "C" int dpm_layernorm_f32(const float *X, int ldx, const float *gamma, const float *beta, const float *post,
                                  int ldpost, float *Y, int ldy, int M, int C, int act, dpm_stream_t stream) {
     if (!X || !gamma || !beta || !Y) return fail(DPM_ERR_ARG, "layernorm: null pointer");

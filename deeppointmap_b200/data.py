@@ -1,15 +1,8 @@
-"""Deterministic synthetic inputs for the hot path and the reduced
-numpy-only preprocessing of a raw KITTI .bin frame (config 1).
-
-Reference behaviour mirrored by `preprocess_bin` (paths relative to /root/reference):
-  dataloader/heads/bin.py:16-17          float32 (N,4) -> xyz, NaN rows dropped
-  dataloader/transforms.py:331-356       VoxelSample(voxel_size, 'first')
-  dataloader/transforms.py:393-397       DistanceSample(min, max)
-  dataloader/transforms.py:400-407       CoordinatesNormalization(ratio)
-"""
+"""Deterministic synthetic inputs for the hot path.  The preprocessing of a raw
+KITTI .bin frame is `deeppointmap_b200.ops.preprocess_frame` (CUDA); its CPU restatement lives with the other
+checkers in oracle/frontend_ref.py."""
 import math
 
-import numpy as np
 import torch
 
 
@@ -68,22 +61,3 @@ def rigid_move(cloud: torch.Tensor, yaw_deg: float, t_m, scale: float = 60.0, ji
         g = torch.Generator().manual_seed(int(seed))
         y = y + jitter_m * torch.randn(y.shape, generator=g, dtype=torch.float64)
     return (y / scale).to(torch.float32).contiguous(), R.to(torch.float32), t.to(torch.float32)
-
-
-def preprocess_bin(raw: np.ndarray, voxel_size: float = 0.3, min_dis: float = 1.0, max_dis: float = 60.0,
-                   ratio: float = 60.0) -> torch.Tensor:
-    """raw float32 (N,4) KITTI frame -> (3, n) fp32 normalised cloud (reduced transform chain:
-    VoxelSample('first') -> DistanceSample -> CoordinatesNormalization; the open3d/pytorch3d
-    OutlierFilter and LowPassFilter of the shipped YAML are skipped)."""
-    xyz = np.asarray(raw, dtype=np.float32).reshape(-1, 4)[:, :3]
-    xyz = xyz[np.isnan(xyz).sum(1) == 0]
-    lo, hi = xyz.min(axis=0), xyz.max(axis=0)
-    X, Y, _ = ((hi - lo) / voxel_size).astype(np.int32) + 1
-    v = ((xyz - lo) / voxel_size).astype(np.int32)
-    vid = (v[:, 0] + v[:, 1] * X + v[:, 2] * X * Y).astype(np.int32)
-    _, first = np.unique(vid, return_index=True)
-    pts = torch.from_numpy(xyz[first])
-    d = torch.norm(pts, p=2, dim=1)
-    pts = pts[(min_dis <= d) & (d <= max_dis)]
-    pts = pts / ratio
-    return pts.T.contiguous()

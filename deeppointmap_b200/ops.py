@@ -165,3 +165,34 @@ def information_matrix(pointcloud_1: torch.Tensor, pointcloud_2: torch.Tensor, S
                                                 info.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(),
                                                 _C.stream_ptr()), "information_matrix")
     return (info, cnt) if return_count else info
+
+
+def preprocess_frame(raw: torch.Tensor, voxel_size: float = 0.3, min_dis: float = 1.0, max_dis: float = 60.0,
+                     ratio: float = 60.0, max_voxels: int = 1 << 26) -> torch.Tensor:
+    """Raw frame -> encoder input on the device: BinReader's NaN-row drop, VoxelSample(voxel_size, 'first'),
+    DistanceSample(min_dis, max_dis), CoordinatesNormalization(ratio) (dataloader/heads/bin.py:16-17,
+    dataloader/transforms.py:331-356, 387-407).  raw (N, C>=3) CUDA fp32 rows (a KITTI .bin is (N,4)) ->
+    (3, n) fp32, points in the reference's order (ascending voxel id).  One host sync (n is data dependent)."""
+    _C.require_cuda(raw)
+    if raw.dim() != 2 or raw.shape[1] < 3:
+        raise ValueError("raw must be (N, C>=3)")
+    r = _f32c(raw)
+    n, stride = r.shape
+    dev = r.device
+    if n == 0:
+        return torch.empty((3, 0), dtype=torch.float32, device=dev)
+    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    lib = _C.lib()
+    nb = lib.dpm_frontend_workspace_bytes(int(max_voxels))
+    if nb == 0:
+        raise ValueError("max_voxels out of range")
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        _C.check(lib.dpm_frontend_f32(r.data_ptr(), n, stride, float(voxel_size), float(min_dis), float(max_dis),
+                                      float(ratio), int(max_voxels), out.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _C.stream_ptr()), "frontend")
+    k = int(cnt.item())
+    if k < 0:
+        raise ValueError(f"the voxel grid of this frame exceeds max_voxels={max_voxels}; crop the frame or raise it")
+    return out[:k].T.contiguous()

@@ -117,6 +117,18 @@ int dpm_linear_ws_f32(const float *X, int ldx, const float *W, int ldw, const fl
                       const float *res, int ldres, float *Y, int ldy, int M, int N, int K, int act,
                       void *workspace, size_t ws_bytes, dpm_stream_t stream);
 
+/* One build_mlp block in one launch (network/encoder/utils.py:358-389: conv -> LayerNorm -> ReLU), also the
+ * decoder's "add & norm" (descriptor_attention.py:33-50):
+ *   Y = act( LayerNorm_N( X W^T + bias + res ) * gamma + beta + post )
+ * The LayerNorm rides in the GEMM epilogue when the row fits one column tile (N <= 256, N % 4 == 0, 16-byte
+ * aligned operands); otherwise the two kernels run back to back through the workspace.  Y may alias res / post.
+ * workspace: dpm_linear_ln_workspace_bytes(M, N, K). */
+size_t dpm_linear_ln_workspace_bytes(int M, int N, int K);
+int dpm_linear_ln_ws_f32(const float *X, int ldx, const float *W, int ldw, const float *bias,
+                         const float *res, int ldres, const float *gamma, const float *beta,
+                         const float *post, int ldpost, float *Y, int ldy, int M, int N, int K, int act,
+                         void *workspace, size_t ws_bytes, dpm_stream_t stream);
+
 int dpm_layernorm_f32(const float *X, int ldx, const float *gamma, const float *beta,
                       const float *post, int ldpost, float *Y, int ldy, int M, int C, int act,
                       dpm_stream_t stream);
@@ -241,6 +253,18 @@ size_t dpm_information_matrix_workspace_bytes(int N1, int N2);
 int dpm_information_matrix_f32(const float *src, int N1, const float *dst, int N2, const float *SE3,
                                float radius, float *info, int32_t *n_corr, void *workspace,
                                size_t ws_bytes, dpm_stream_t stream);
+
+/* Raw frame -> encoder input on the device: BinReader's NaN-row drop
+ * (dataloader/heads/bin.py:16-17), VoxelSample(voxel_size, 'first') (dataloader/transforms.py:331-356),
+ * DistanceSample(min_dis, max_dis) (:387-397) and CoordinatesNormalization(ratio) (:400-407).
+ * raw: N rows of `stride` floats (x, y, z first; 4 for a KITTI .bin).  out_rows: room for N x 3 floats; the
+ * first *count rows are the surviving points / ratio in ascending voxel-id order (the reference's order).
+ * count (device int32) = -1 when the voxel grid of this frame has more than max_voxels cells (nothing is
+ * written then; crop the frame or raise max_voxels).  No host sync. */
+size_t dpm_frontend_workspace_bytes(long long max_voxels);
+int dpm_frontend_f32(const float *raw, int N, int stride, float voxel_size, float min_dis, float max_dis,
+                     float ratio, long long max_voxels, float *out_rows, int32_t *count, void *workspace,
+                     size_t ws_bytes, dpm_stream_t stream);
 
 #ifdef __cplusplus
 }

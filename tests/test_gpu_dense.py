@@ -68,6 +68,30 @@ def test_linear_presplit_weights(M, N, K, ldw):
                                        ws.data_ptr(), 16, _C.stream_ptr()))
 
 
+@pytest.mark.parametrize("M,N,K", [(16384, 256, 256), (1000, 32, 128), (4096, 64, 32), (300, 128, 512), (129, 256, 64),
+                                   (77, 512, 128), (50, 100, 36), (1, 32, 4), (640, 48, 16)])
+@pytest.mark.parametrize("mode", ["plain", "res+post", "inplace"])
+def test_linear_layernorm_fused(M, N, K, mode):
+    """conv -> LayerNorm (-> +post) -> ReLU in one launch for N <= 256 (epilogue LayerNorm), two kernels
+    beyond; `inplace` is the decoder's add & norm: Y aliases the residual."""
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    X, W = torch.randn(M, K, generator=g).to(DEV), (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b, gam, bet = (torch.randn(N, generator=g).to(DEV) for _ in range(3))
+    res = torch.randn(M, N, generator=g).to(DEV) if mode != "plain" else None
+    post = torch.randn(M, N, generator=g).to(DEV) if mode != "plain" else None
+    y = X.double() @ W.double().T + b.double() + (res.double() if res is not None else 0)
+    ref = F.layer_norm(y, (N,), gam.double(), bet.double(), 1e-5) + (post.double() if post is not None else 0)
+    ref = F.relu(ref)
+    lib = _C.lib()
+    nb = lib.dpm_linear_ln_workspace_bytes(M, N, K)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    Y = res if mode == "inplace" else torch.empty(M, N, device=DEV)
+    _C.check(lib.dpm_linear_ln_ws_f32(X.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), _C.ptr(res), N, gam.data_ptr(),
+                                      bet.data_ptr(), _C.ptr(post), N, Y.data_ptr(), N, M, N, K, _C.ACT_RELU,
+                                      ws.data_ptr(), nb, _C.stream_ptr()))
+    assert rel_err(Y, ref) < 2e-5
+
+
 @pytest.mark.parametrize("M,C", [(1, 32), (1000, 32), (77, 128), (16, 2048), (4096, 256), (5, 48)])
 def test_layernorm(M, C):
     g = torch.Generator().manual_seed(C)

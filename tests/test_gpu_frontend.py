@@ -1,0 +1,65 @@
+"""GPU parity of the preprocessing front-end (dpm_frontend_f32) vs oracle/frontend_ref.py: the SAME points in
+the SAME order, bit for bit (integer / index work; the only floating-point outputs are exact divisions)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from deeppointmap_b200 import data, ops
+from oracle import frontend_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _raw_frame(seed: int, n: int) -> np.ndarray:
+    """KITTI-like raw rows in metres: structured cloud out to 75 m (so DistanceSample has work), near-duplicates
+    inside voxels (so 'first' has work), intensity column, a few NaN rows"""
+    g = torch.Generator().manual_seed(seed)
+    base = data.kitti_shape_cloud(seed, max(1, n // 2)) * 75.0
+    dup = base[:, torch.randint(0, base.shape[1], (n - n // 2,), generator=g)] + 0.05 * torch.randn(3, n - n // 2, generator=g)
+    xyz = torch.cat([base, dup], dim=1)[:, torch.randperm(n, generator=g)]
+    raw = torch.cat([xyz, torch.rand(1, n, generator=g)], dim=0).T.contiguous().numpy().astype(np.float32)
+    if n >= 74:
+        raw[:: n // 37, 1] = np.nan
+    return raw
+
+
+@pytest.mark.parametrize("n", [122000, 65536, 5000, 64, 1])
+def test_frontend_bit_exact(n):
+    raw = _raw_frame(n, n)
+    want = frontend_ref.preprocess_bin(raw)
+    got = ops.preprocess_frame(torch.from_numpy(raw).to(DEV)).cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
+
+
+def test_frontend_golden_other_parameters_and_limits():
+    g = np.load(os.path.join(GOLDEN, "frontend.npz"))
+    got = ops.preprocess_frame(torch.from_numpy(g["raw"]).to(DEV)).cpu()
+    assert torch.equal(got, torch.from_numpy(g["out"]))
+    raw = _raw_frame(3, 30000)
+    for voxel, lo, hi, ratio in ((0.5, 2.0, 40.0, 40.0), (0.1, 0.0, 1000.0, 1.0)):
+        want = frontend_ref.preprocess_bin(raw, voxel, lo, hi, ratio)
+        got = ops.preprocess_frame(torch.from_numpy(raw).to(DEV), voxel, lo, hi, ratio, max_voxels=1 << 28).cpu()
+        assert torch.equal(got, want)
+    xyz3 = torch.from_numpy(np.ascontiguousarray(raw[:, :3])).to(DEV)                 # (N,3) rows work too
+    assert torch.equal(ops.preprocess_frame(xyz3).cpu(), frontend_ref.preprocess_bin(raw))
+    allnan = torch.full((100, 4), float("nan"), device=DEV)
+    assert ops.preprocess_frame(allnan).shape == (3, 0)
+    with pytest.raises(ValueError):                                                     # one far outlier: grid too large
+        far = torch.from_numpy(raw).to(DEV).clone()
+        far[0, 0] = 1.0e6
+        ops.preprocess_frame(far, max_voxels=1 << 20)
+
+
+def test_frontend_feeds_the_encoder(cfg):
+    """raw rows -> preprocess_frame -> Encoder: the front-end's output is a valid encoder input"""
+    from deeppointmap_b200 import Encoder
+    enc = Encoder(cfg).eval().to(DEV)
+    pts = ops.preprocess_frame(torch.from_numpy(_raw_frame(9, 100000)).to(DEV))
+    assert pts.shape[0] == 3 and pts.shape[1] > 4096 and float(pts.norm(dim=0).max()) <= 1.0 + 1e-6
+    coor, fea, pad = enc(pts[None], torch.zeros(1, pts.shape[1], dtype=torch.bool, device=DEV))
+    assert coor.shape == (1, 3, 256) and fea.shape == (1, 128, 256) and not bool(pad.any())

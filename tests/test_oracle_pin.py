@@ -231,3 +231,51 @@ def test_information_matrix_oracle_matches_golden():
                                                 torch.from_numpy(g[name + "_T"]), float(g[name + "_radius"]))
         want = torch.from_numpy(g[name + "_info"])
         assert float((got - want).abs().max()) <= 1e-5 * max(float(want.abs().max()), 1e-30), name
+
+
+# ---- preprocessing front-end ---------------------------------------------------
+def _reference_transforms():
+    """dataloader/transforms.py of the reference with a stub `open3d` (only its filters need the real one)"""
+    import importlib
+    import types
+    saved = {k: sys.modules.get(k) for k in ("open3d", "pytorch3d")}
+    if saved["open3d"] is None:
+        sys.modules["open3d"] = types.ModuleType("open3d")
+    sys.modules["pytorch3d"] = None
+    sys.path.insert(0, REF)
+    try:
+        RT = importlib.import_module("dataloader.transforms")
+    finally:
+        sys.path.remove(REF)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return RT
+
+
+@needs_ref
+@pytest.mark.reference
+def test_frontend_matches_reference_transforms():
+    """oracle/frontend_ref.py vs the reference's own BinReader rule + VoxelSample('first') + DistanceSample +
+    CoordinatesNormalization on a shipped sample frame: identical points in identical order."""
+    from oracle import frontend_ref
+    RT = _reference_transforms()
+    raw = np.fromfile(f"{REF}/data/sample/seq06/velodyne/000003.bin", dtype=np.float32).reshape(-1, 4)
+    xyz = raw[:, :3]
+    xyz = xyz[np.isnan(xyz).sum(1) == 0]                      # heads/bin.py:16-17
+    pcd = RT.PointCloud(xyz.copy())
+    for t in (RT.VoxelSample(0.3, "first"), RT.DistanceSample(1, 60), RT.CoordinatesNormalization(60)):
+        pcd = t(pcd)
+    want = pcd.xyz.T.contiguous()
+    got = frontend_ref.preprocess_bin(raw)
+    assert got.shape == want.shape and got.shape[1] > 10000
+    assert torch.equal(got, want)
+
+
+def test_frontend_oracle_matches_golden():
+    from oracle import frontend_ref
+    g = np.load(os.path.join(ROOT, "tests", "golden", "frontend.npz"))
+    got = frontend_ref.preprocess_bin(g["raw"])
+    assert torch.equal(got, torch.from_numpy(g["out"]))
