@@ -216,7 +216,7 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 // new sample touches -- spatial neighbours, i.e. consecutive ids -- spread over all warps.  An
 // owner keeps its buckets' boxes, largest min-distances and the points attaining them in
 // registers.  Per pick: every owner tests its 1024/T boxes; a warp then updates its touched
-// buckets, one per slot per round with all loads of a round in flight together (one L2 round
+// buckets, up to D per slot per round with all loads of a round in flight together (one L2 round
 // trip per round); warp arg-max -> shared memory -> one barrier -> every warp reduces the W
 // records.  Measured on B200 (N = 65536, K = 4096): T = 1024 / 512 / 256 / 128 -> 4.98 / 5.3 /
 // 7.1 / 11.3 ms -- a pick is bound by the dependent-instruction latency of ONE warp's chain
@@ -227,8 +227,11 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 // touched buckets 1 130 (L2 round trip ~800 + update), warp arg-max 400, block arg-max 260; the other
 // warps wait at the barrier for the ones that had a round.  Replacing the second REDUX of an arg-max by a
 // ballot + shuffle fast path for unique maxima was slower (divergent branch around warp collectives).
+// Keeping a 4096-point level entirely in shared memory (no L2 round trip at all) does not change its
+// 0.75 us per pick: what bounds a pick is the ~100-instruction dependent chain of tests and three levels of
+// arg-max (64 points -> bucket, 32 buckets -> warp, 32 warps -> block), not where the points live.
 // ---------------------------------------------------------------------------------------
-template <int PPL, int T, int BPT>
+template <int PPL, int T, int BPT, int D>
 __global__ void __launch_bounds__(T, 1)
 fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
                 const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
@@ -323,22 +326,26 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
             anym |= mask[s];
         }
         while (anym) {
-            // one round: the first touched bucket of every slot; all their loads are issued before the first
+            // one round: the first D touched buckets of every slot; all their loads are issued before the first
             // one is consumed
-            int Ls[BPT];
-            float4 p[BPT][PPL];
-            float m[BPT][PPL];
+            int Ls[BPT * D];
+            float4 p[BPT * D][PPL];
+            float m[BPT * D][PPL];
 #pragma unroll
             for (int s = 0; s < BPT; ++s) {
-                Ls[s] = -1;
-                if (mask[s]) {
-                    Ls[s] = __ffs(mask[s]) - 1;
-                    mask[s] &= mask[s] - 1;
-                    const int base = (s * T + Ls[s] * W + warp) * BS + lane;
 #pragma unroll
-                    for (int j = 0; j < PPL; ++j) {
-                        p[s][j] = P[base + j * 32];
-                        m[s][j] = M[base + j * 32];
+                for (int d = 0; d < D; ++d) {
+                    const int q = s * D + d;
+                    Ls[q] = -1;
+                    if (mask[s]) {
+                        Ls[q] = __ffs(mask[s]) - 1;
+                        mask[s] &= mask[s] - 1;
+                        const int base = (s * T + Ls[q] * W + warp) * BS + lane;
+#pragma unroll
+                        for (int j = 0; j < PPL; ++j) {
+                            p[q][j] = P[base + j * 32];
+                            m[q][j] = M[base + j * 32];
+                        }
                     }
                 }
             }
@@ -346,28 +353,32 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
 #pragma unroll
             for (int s = 0; s < BPT; ++s) {
                 anym |= mask[s];
-                if (Ls[s] < 0) continue;  // warp-uniform
-                const int base = (s * T + Ls[s] * W + warp) * BS + lane;
-                float bestv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
-                unsigned besti = 0xffffffffu;
 #pragma unroll
-                for (int j = 0; j < PPL; ++j) {
-                    const float d = d2_exact(sx, sy, sz, p[s][j].x, p[s][j].y, p[s][j].z);
-                    const float nm = fminf(m[s][j], d);
-                    if (nm < m[s][j]) M[base + j * 32] = nm;
-                    const unsigned id = __float_as_uint(p[s][j].w);
-                    if (nm > bestv || (nm == bestv && id < besti)) {
-                        bestv = nm; besti = id; bx = p[s][j].x; by = p[s][j].y; bz = p[s][j].z;
+                for (int d = 0; d < D; ++d) {
+                    const int q = s * D + d;
+                    if (Ls[q] < 0) continue;  // warp-uniform
+                    const int base = (s * T + Ls[q] * W + warp) * BS + lane;
+                    float bestv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+                    unsigned besti = 0xffffffffu;
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) {
+                        const float dd = d2_exact(sx, sy, sz, p[q][j].x, p[q][j].y, p[q][j].z);
+                        const float nm = fminf(m[q][j], dd);
+                        if (nm < m[q][j]) M[base + j * 32] = nm;
+                        const unsigned id = __float_as_uint(p[q][j].w);
+                        if (nm > bestv || (nm == bestv && id < besti)) {
+                            bestv = nm; besti = id; bx = p[q][j].x; by = p[q][j].y; bz = p[q][j].z;
+                        }
                     }
+                    const unsigned bits = __float_as_uint(bestv);  // bestv >= 0: the bit pattern is order preserving
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
+                    const unsigned wmin = __reduce_min_sync(0xffffffffu, bits == wmax ? besti : 0xffffffffu);
+                    const int src = __ffs(__ballot_sync(0xffffffffu, bits == wmax && besti == wmin)) - 1;
+                    const float wx = __shfl_sync(0xffffffffu, bx, src);
+                    const float wy = __shfl_sync(0xffffffffu, by, src);
+                    const float wz = __shfl_sync(0xffffffffu, bz, src);
+                    if (lane == Ls[q]) { maxbits[s] = wmax; argidx[s] = wmin; ax[s] = wx; ay[s] = wy; az[s] = wz; }
                 }
-                const unsigned bits = __float_as_uint(bestv);  // bestv >= 0: the bit pattern is order preserving
-                const unsigned wmax = __reduce_max_sync(0xffffffffu, bits);
-                const unsigned wmin = __reduce_min_sync(0xffffffffu, bits == wmax ? besti : 0xffffffffu);
-                const int src = __ffs(__ballot_sync(0xffffffffu, bits == wmax && besti == wmin)) - 1;
-                const float wx = __shfl_sync(0xffffffffu, bx, src);
-                const float wy = __shfl_sync(0xffffffffu, by, src);
-                const float wz = __shfl_sync(0xffffffffu, bz, src);
-                if (lane == Ls[s]) { maxbits[s] = wmax; argidx[s] = wmin; ax[s] = wx; ay[s] = wy; az[s] = wz; }
             }
         }
         // ---- arg-max over all buckets: (value desc, original index asc) -------------------------
@@ -421,7 +432,7 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
 #define DPM_FG_ARGS g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, new_pad, new_len32
 #define DPM_FG_CASE(p)                                                \
     case p:                                                           \
-        fps_grid_kernel<p, 1024, 1><<<B, 1024, 0, st>>>(DPM_FG_ARGS); \
+        fps_grid_kernel<p, 1024, 1, (p <= 2 ? 2 : 1)><<<B, 1024, 0, st>>>(DPM_FG_ARGS); \
         break;
     switch (ppl) {
         DPM_FG_CASE(1) DPM_FG_CASE(2) DPM_FG_CASE(4) DPM_FG_CASE(8)
