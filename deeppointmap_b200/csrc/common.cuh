@@ -16,6 +16,7 @@ int fail(int code, const char *fmt, ...);
 // so consecutive events bracket each kernel (everything of one call is on one stream).
 void count_launch(const char *tag, cudaStream_t st);
 void prof_note(long long a, long long b);
+bool prof_active();
 void prof_mark(cudaStream_t st);  // call boundary: time since the previous record is not kernel time  // detail columns of the NEXT launch record
 
 #define DPM_CHECK_CUDA(expr)                                                                   \

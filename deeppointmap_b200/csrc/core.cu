@@ -46,6 +46,8 @@ void count_launch(const char *tag, cudaStream_t st) {
     if (g_prof_on) prof_record(tag, st);
 }
 
+bool prof_active() { return g_prof_on; }
+
 // start of a C-ABI call: the stream time since the previous record is host-side gap, not kernel time
 void prof_mark(cudaStream_t st) {
     if (g_prof_on) prof_record("host_gap", st);
