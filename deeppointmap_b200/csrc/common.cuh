@@ -132,7 +132,6 @@ int pack_xyz4_launch(const float *src, int B, int N, int D, float4 *dst, cudaStr
 int lengths_to_i32_launch(const int64_t *len64, int B, int N, int *len32, cudaStream_t st);
 int linear_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res, int ldres,
                   float *Y, int ldy, int M, int N, int K, int act, cudaStream_t st);
-void set_unit_rows(int n);  // rows per independent unit for the following linear launches (0 = unknown)
 // tcgen05 3xTF32 path (gemm_tc.cu); linear_launch routes to it when eligible
 bool linear_tc_eligible(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, int M, int N, int K);
 int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,

@@ -7,8 +7,6 @@
 // self/cross attention are one launch over 2P (query-range, key-range) problems.
 // Data-dependent shapes of the reference (offset filter, sigma clipping) are restated with
 // counts + masks on the device: there is no host sync anywhere in here.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace dpm {
@@ -69,135 +67,7 @@ int posenc_launch(const float *xyz, int ldx, const float *dim_t, int npf, float 
 }
 
 // ---------------------------------------------------------------------------------------
-// multi-head attention core, head_dim 32, fp32, flash-style online softmax.
-// block = 32 queries (lane = query) x 4 warps splitting the keys of each 256-key chunk.
-// ---------------------------------------------------------------------------------------
-constexpr int ATT_KC = 256;
-
-__global__ void __launch_bounds__(128)
-attention_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__ Kp, int ldk,
-                 const float *__restrict__ Vp, int ldv, float *__restrict__ O, int ldo, const int *__restrict__ prob,
-                 int M, int N, int mode) {
-    extern __shared__ __align__(16) float att_smem[];
-    float *Ks = att_smem;                 // [ATT_KC][32]
-    float *Vs = att_smem + ATT_KC * 32;   // [ATT_KC][32]
-    __shared__ float mb[4][32][35];
-
-    const int z = blockIdx.z, head = blockIdx.y;
-    int q0, Lq, k0, Lk;
-    if (prob) {
-        q0 = prob[4 * z]; Lq = prob[4 * z + 1]; k0 = prob[4 * z + 2]; Lk = prob[4 * z + 3];
-    } else {
-        const int p = z >> 1, side = z & 1, base = p * (M + N);
-        q0 = base + (side ? M : 0);
-        Lq = side ? N : M;
-        const int kvside = mode ? !side : side;  // mode 0: self, 1: cross
-        k0 = base + (kvside ? M : 0);
-        Lk = kvside ? N : M;
-    }
-    if (blockIdx.x * 32 >= Lq) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qi = blockIdx.x * 32 + lane;
-    const bool qvalid = qi < Lq;
-
-    float qv[32], acc[32];
-    {
-        const float *qp = Q + (size_t)(q0 + (qvalid ? qi : 0)) * ldq + head * 32;
-        const float scale = 0.17677669529663687f;  // sqrt(1/32)
-#pragma unroll
-        for (int d4 = 0; d4 < 8; ++d4) {
-            const float4 t = *reinterpret_cast<const float4 *>(qp + 4 * d4);
-            qv[4 * d4] = t.x * scale; qv[4 * d4 + 1] = t.y * scale; qv[4 * d4 + 2] = t.z * scale; qv[4 * d4 + 3] = t.w * scale;
-        }
-#pragma unroll
-        for (int d = 0; d < 32; ++d) acc[d] = 0.f;
-    }
-    float m = -__int_as_float(0x7f800000), l = 0.f;
-
-    for (int c0 = 0; c0 < Lk; c0 += ATT_KC) {
-        const int cn = min(ATT_KC, Lk - c0);
-        __syncthreads();
-        for (int e = tid; e < cn * 8; e += 128) {
-            const int key = e >> 3, part = e & 7;
-            const size_t row = (size_t)(k0 + c0 + key);
-            reinterpret_cast<float4 *>(Ks)[e] = *reinterpret_cast<const float4 *>(Kp + row * ldk + head * 32 + 4 * part);
-            reinterpret_cast<float4 *>(Vs)[e] = *reinterpret_cast<const float4 *>(Vp + row * ldv + head * 32 + 4 * part);
-        }
-        __syncthreads();
-        const int per = (cn + 3) / 4;
-        const int jb = warp * per, je = min(cn, jb + per);
-        for (int j = jb; j < je; j += 4) {
-            float s[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int jj = min(j + u, je - 1);
-                const float4 *kr = reinterpret_cast<const float4 *>(Ks + jj * 32);
-                float a = 0.f;
-#pragma unroll
-                for (int d4 = 0; d4 < 8; ++d4) {
-                    const float4 kk = kr[d4];
-                    a = fmaf(qv[4 * d4], kk.x, a);
-                    a = fmaf(qv[4 * d4 + 1], kk.y, a);
-                    a = fmaf(qv[4 * d4 + 2], kk.z, a);
-                    a = fmaf(qv[4 * d4 + 3], kk.w, a);
-                }
-                s[u] = (j + u < je) ? a : -__int_as_float(0x7f800000);
-            }
-            const float mx = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
-            const float corr = expf(m - mx);
-            l *= corr;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) acc[d] *= corr;
-            m = mx;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float pexp = expf(s[u] - mx);
-                l += pexp;
-                const int jj = min(j + u, je - 1);
-                const float4 *vr = reinterpret_cast<const float4 *>(Vs + jj * 32);
-#pragma unroll
-                for (int d4 = 0; d4 < 8; ++d4) {
-                    const float4 vv = vr[d4];
-                    acc[4 * d4] = fmaf(pexp, vv.x, acc[4 * d4]);
-                    acc[4 * d4 + 1] = fmaf(pexp, vv.y, acc[4 * d4 + 1]);
-                    acc[4 * d4 + 2] = fmaf(pexp, vv.z, acc[4 * d4 + 2]);
-                    acc[4 * d4 + 3] = fmaf(pexp, vv.w, acc[4 * d4 + 3]);
-                }
-            }
-        }
-    }
-    // merge the 4 key-slices
-    mb[warp][lane][32] = m;
-    mb[warp][lane][33] = l;
-#pragma unroll
-    for (int d = 0; d < 32; ++d) mb[warp][lane][d] = acc[d];
-    __syncthreads();
-    float mm = mb[0][lane][32];
-#pragma unroll
-    for (int w = 1; w < 4; ++w) mm = fmaxf(mm, mb[w][lane][32]);
-    float e[4], L = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        e[w] = expf(mb[w][lane][32] - mm);
-        L = fmaf(mb[w][lane][33], e[w], L);
-    }
-    if (qvalid) {
-        float *op = O + (size_t)(q0 + qi) * ldo + head * 32 + warp * 8;
-        float r[8];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) {
-            float a = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) a = fmaf(mb[w][lane][warp * 8 + d], e[w], a);
-            r[d] = a / L;
-        }
-        *reinterpret_cast<float4 *>(op) = make_float4(r[0], r[1], r[2], r[3]);
-        *reinterpret_cast<float4 *>(op + 4) = make_float4(r[4], r[5], r[6], r[7]);
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// the same attention on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 error
+// multi-head attention core (head_dim 32) on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 error
 // compensation (x = hi + lo, products hi*hi + hi*lo + lo*hi), fp32 accumulation, flash-style
 // online softmax in registers.  CTA = 128 queries (8 warps x 16 rows) x one head; keys / values
 // are staged 64 at a time in shared memory already split into hi / lo (row stride 36 floats:
@@ -375,22 +245,8 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
                      const int *prob, int nprob, int maxLq, int M, int N, int mode, int heads, cudaStream_t st) {
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
     if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
-    const size_t smem = 2 * (size_t)ATT_KC * 32 * sizeof(float);
-    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
-    const unsigned long long devbit = 1ull << (current_device() & 63);
-    if (!(configured & devbit)) {
-        DPM_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured |= devbit;
-    }
-    static const bool simt = getenv("DPM_ATT_SIMT") != nullptr;  // developer A/B switch
-    if (!simt) {
-        dim3 gtc((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
-        attention_tc_kernel<<<gtc, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
-        DPM_CHECK_LAUNCH("attention", st);
-        return DPM_OK;
-    }
-    dim3 grid((maxLq + 31) / 32, heads, nprob);
-    attention_kernel<<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
+    dim3 grid((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
+    attention_tc_kernel<<<grid, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
     DPM_CHECK_LAUNCH("attention", st);
     return DPM_OK;
 }
@@ -981,7 +837,6 @@ static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float
     dec_unpack_kernel<<<g, 256, 0, st>>>(src, dst, M, N, Cf, fea, xyz);
     DPM_CHECK_LAUNCH("dec_unpack", st);
     DPM_TRY(posenc_launch(reinterpret_cast<const float *>(xyz), 4, w.dim_t, npf, pos, R, C, st));
-    set_unit_rows(M < N ? M : N);  // path choice per pair, independent of how many pairs are batched
     // x = projection(fea) + pos   (the "+ pos" of the first layer, descriptor_attention.py:31)
     DPM_TRY(linear_launch(fea, Cf, w.proj_w, Cf, w.proj_b, pos, C, x, C, R, C, Cf, DPM_ACT_NONE, st));
     for (int l = 0; l < d->attention_layers; ++l) {
@@ -1040,7 +895,6 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     if (dry) return DPM_OK;
 
     // similarity head + L2 normalise (decoder.py:181-185)
-    set_unit_rows(M < N ? M : N);
     DPM_TRY(linear_launch(F, C, w.sim0_w, C, w.sim0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(h, C, w.sim2_w, C, w.sim2_b, nullptr, 0, sim, C, R, C, C, DPM_ACT_NONE, st));
     l2norm_rows_kernel<<<(R + 7) / 8, 256, 0, st>>>(sim, R, C);
@@ -1071,7 +925,6 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     pair_gather_kernel<<<dim3(K2, P, 1), 256, 0, st>>>(F, C, M, N, k, si, di, X);
     DPM_CHECK_LAUNCH("pair_gather", st);
     const int RO = P * K2;
-    set_unit_rows(K2);
     DPM_TRY(linear_launch(X, 2 * C, w.off0_w, 2 * C, w.off0_b, nullptr, 0, o1, C, RO, C, 2 * C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(o1, C, w.off2_w, C, w.off2_b, nullptr, 0, o2, C / 2, RO, C / 2, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(X, 2 * C, w.offd_w, 2 * C, w.offd_b, nullptr, 0, oi, C / 4, RO, C / 4, 2 * C, DPM_ACT_NONE, st));
@@ -1102,12 +955,10 @@ static int loop_run(const dpm_decoder_desc *d, const float *const *weights, cons
     float *logit = a.get<float>((size_t)P);
     if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "loop_detection: workspace too small");
     if (dry) return DPM_OK;
-    set_unit_rows(M < N ? M : N);
     DPM_TRY(linear_launch(F, C, w.lp0_w, C, w.lp0_b, nullptr, 0, h, C, R, C, C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(h, C, w.lp2_w, C, w.lp2_b, nullptr, 0, g, C, R, C, C, DPM_ACT_NONE, st));
     token_mean_kernel<<<dim3(P, 2, 1), 256, 0, st>>>(g, C, M, N, mean);
     DPM_CHECK_LAUNCH("token_mean", st);
-    set_unit_rows(1);
     DPM_TRY(linear_launch(mean, 2 * C, w.lq0_w, 2 * C, w.lq0_b, nullptr, 0, p1, 2 * C, P, 2 * C, 2 * C, DPM_ACT_RELU, st));
     DPM_TRY(linear_launch(p1, 2 * C, w.lq2_w, 2 * C, w.lq2_b, nullptr, 0, logit, 1, P, 1, 2 * C, DPM_ACT_NONE, st));
     sigmoid_kernel<<<(P + 127) / 128, 128, 0, st>>>(logit, prob, P);

@@ -86,12 +86,6 @@ linear_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W,
     }
 }
 
-// Rows of one independent unit (cloud / descriptor pair) in the following linear launches.  The
-// tensor-core path is chosen from THIS, not from the batched row count, so a unit's result is
-// bit-identical whatever else shares the batch.  0 = unknown (use the launch's M).
-static thread_local int g_unit_rows = 0;
-void set_unit_rows(int n) { g_unit_rows = n; }
-
 int linear_batched_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW,
                           const float *bias, const float *res, int ldres, float *Y, int ldy, long long sY, int M,
                           int N, int K, int nbatch, int act, cudaStream_t st) {
@@ -481,7 +475,6 @@ using namespace dpm;
 extern "C" int dpm_linear_f32(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res,
                               int ldres, float *Y, int ldy, int M, int N, int K, int act, dpm_stream_t stream) {
     if (!X || !W || !Y) return fail(DPM_ERR_ARG, "linear: null pointer");
-    set_unit_rows(0);
     split_begin();  // no pre-split weights outside the encoder / decoder calls
     return linear_launch(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, (cudaStream_t)stream);
 }
@@ -497,7 +490,6 @@ extern "C" int dpm_linear_ws_f32(const float *X, int ldx, const float *W, int ld
                                  dpm_stream_t stream) {
     if (!X || !W || !Y || !ws) return fail(DPM_ERR_ARG, "linear: null pointer");
     if (ws_bytes < dpm_linear_workspace_bytes(N, K)) return fail(DPM_ERR_WORKSPACE, "linear: workspace too small");
-    set_unit_rows(0);
     Arena a(ws, ws_bytes);
     split_begin();
     split_add(a, W, N, K, ldw);
@@ -521,7 +513,6 @@ extern "C" int dpm_linear_ln_ws_f32(const float *X, int ldx, const float *W, int
     if (!X || !W || !Y || !gamma || !beta || !ws) return fail(DPM_ERR_ARG, "linear_ln: null pointer");
     if (M <= 0 || N <= 0 || K <= 0) return fail(DPM_ERR_SHAPE, "linear_ln: bad shape M=%d N=%d K=%d", M, N, K);
     if (ws_bytes < dpm_linear_ln_workspace_bytes(M, N, K)) return fail(DPM_ERR_WORKSPACE, "linear_ln: workspace too small");
-    set_unit_rows(0);
     Arena a(ws, ws_bytes);
     split_begin();
     split_add(a, W, N, K, ldw);

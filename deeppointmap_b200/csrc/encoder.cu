@@ -303,7 +303,6 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
                                               dst.fea, B, src.n, S, K0, Cout, st));
             } else {
                 // per-point half of the 1x1 conv: Z = fea . Wfea^T + b   (weight columns [0:Cin] = features)
-                set_unit_rows(src.n);
                 DPM_TRY(linear_launch(src.fea, Cin, Wsa, Cin + 3, bsa, nullptr, 0, Z, Cout, B * src.n, Cout, Cin,
                                       DPM_ACT_NONE, st));
                 DPM_TRY(group_launch(Z, src.xyz, dst.xyz, gidx, Wsa + Cin, Cin + 3, gsa, besa, (float)r0, dst.fea, B, src.n, S, K0,
@@ -342,7 +341,6 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
                     DPM_CHECK_CUDA(cudaMemcpyAsync(trace_knn + knn_off, g2, sizeof(int32_t) * (size_t)B * S * K,
                                                    cudaMemcpyDeviceToDevice, st));
                 }
-                set_unit_rows(S);
                 DPM_TRY(linear_launch(dst.fea, Cout, Wla, Cout + 3, bla, nullptr, 0, Z2, Cout, B * S, Cout, Cout,
                                       DPM_ACT_NONE, st));
                 DPM_TRY(group_launch(Z2, dst.xyz, dst.xyz, g2, Wla + Cout, Cout + 3, gla, bela, (float)r, la, B, S, S, K, Cout, st));
@@ -378,7 +376,6 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
         const float *W2 = W(), *b2 = W(), *g2 = W(), *be2 = W();
         if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
         if (!dry) {
-            set_unit_rows(l1.n);
             DPM_TRY(fp_interp_launch(l1.xyz, l2.xyz, l1.fea, l2.fea, l2.pad, cat, B, l1.n, l2.n, l1.c, l2.c, st));
             DPM_TRY(linear_ln_launch(cat, Ccat, W1, Ccat, b1, nullptr, 0, g1, be1, nullptr, 0, h1, h1, up_out, B * l1.n, up_out,
                                      Ccat, DPM_ACT_RELU, st));

@@ -1,0 +1,56 @@
+"""The reference's multi-thread mode calls the encoder from one host thread and the decoder from three others
+(system/core.py:93-103), multi-agent mode runs four model pairs on four threads (infer_multiagents.py:100-113).
+The library keeps its per-call state (pre-split weight registry, forked streams, workspaces, error string,
+launch profile) thread-local: concurrent calls from several threads and streams must give bit-identical
+results to the same calls made one after another."""
+import copy
+import threading
+
+import pytest
+import torch
+
+from deeppointmap_b200 import Decoder, Encoder, data
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_concurrent_threads_match_sequential(cfg, checkpoint):
+    enc, dec = Encoder(cfg).eval(), Decoder(cfg).eval()
+    enc.load_state_dict(checkpoint["encoder"], strict=True)
+    dec.load_state_dict(checkpoint["decoder"], strict=True)
+    enc, dec = enc.to(DEV), dec.to(DEV)
+    models = [(enc, dec)] + [(copy.deepcopy(enc), copy.deepcopy(dec)) for _ in range(3)]  # thread 0 shares, 1-3 own copies
+    clouds = [torch.stack([data.kitti_shape_cloud(10 * t + i, 8192) for i in range(3)]).to(DEV) for t in range(4)]
+
+    def work(t, out):
+        e, d = models[t]
+        st = torch.cuda.Stream(device=DEV)
+        with torch.cuda.stream(st), torch.no_grad():
+            res = []
+            for rep in range(3):
+                desc = e.descriptors(clouds[t], None, coor_scale=cfg.coor_scale)
+                r, conf = d.registration_forward_batch(desc[:2], desc[1:], 0.5)
+                prob = d.loop_detection_forward(desc[:2], desc[1:])
+                res.append((desc.clone(), r.clone(), prob.clone()))
+            st.synchronize()
+        out[t] = res
+
+    seq = {}
+    for t in range(4):
+        work(t, seq)
+    par = {}
+    threads = [threading.Thread(target=work, args=(t, par)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert sorted(par) == [0, 1, 2, 3]
+    for t in range(4):
+        for (d0, r0, p0), (d1, r1, p1) in zip(seq[t], par[t]):
+            assert torch.equal(d0, d1), f"thread {t}: descriptors differ under concurrency"
+            assert torch.equal(r0, r1), f"thread {t}: poses differ under concurrency"
+            assert torch.equal(p0, p1), f"thread {t}: loop probabilities differ under concurrency"
+    # and repeated calls are deterministic
+    for t in range(4):
+        assert torch.equal(seq[t][0][0], seq[t][2][0]) and torch.equal(seq[t][0][1], seq[t][2][1])
