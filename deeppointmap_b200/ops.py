@@ -196,3 +196,27 @@ def preprocess_frame(raw: torch.Tensor, voxel_size: float = 0.3, min_dis: float 
     if k < 0:
         raise ValueError(f"the voxel grid of this frame exceeds max_voxels={max_voxels}; crop the frame or raise it")
     return out[:k].T.contiguous()
+
+
+def map_tile(store: torch.Tensor, ids, poses: torch.Tensor, center: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Scan-to-map input stage on the device (PoseGraph.__global_mapping + the centring of
+    global_map_query_graph, system/modules/pose_graph.py:373-409, 499-511).  store (n, Cd, S) device-resident
+    descriptor sets, ids (m,) key-frame slots, poses (m,4,4) their SE3_pred, center (4,4) or None ->
+    (Cd, m*S) map tile = the `dst_descriptor` of Decoder.registration_forward.  SURVEY.md section 8f rank 3."""
+    _C.require_cuda(store)
+    if store.dim() != 3 or store.shape[1] < 4:
+        raise ValueError("store must be (n, Cd>=4, S)")
+    st = _f32c(store)
+    dev = st.device
+    idt = torch.as_tensor(ids, dtype=torch.int32).to(dev).contiguous().view(-1)
+    m = int(idt.numel())
+    P = poses.to(device=dev, dtype=torch.float32).contiguous().view(-1, 16)
+    if m == 0 or P.shape[0] != m:
+        raise ValueError("ids and poses must have the same non-zero length")
+    C = None if center is None else center.to(device=dev, dtype=torch.float32).contiguous().view(16)
+    n, Cd, S = st.shape
+    tile = torch.empty((Cd, m * S), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _C.check(_C.lib().dpm_map_tile_f32(st.data_ptr(), n, Cd, S, idt.data_ptr(), P.data_ptr(), _C.ptr(C), m,
+                                           tile.data_ptr(), _C.stream_ptr()), "map_tile")
+    return tile

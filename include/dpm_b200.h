@@ -266,6 +266,14 @@ int dpm_frontend_f32(const float *raw, int N, int stride, float voxel_size, floa
                      float ratio, long long max_voxels, float *out_rows, int32_t *count, void *workspace,
                      size_t ws_bytes, dpm_stream_t stream);
 
+/* Scan-to-map input stage: PoseGraph.__global_mapping + the centring of
+ * global_map_query_graph, system/modules/pose_graph.py:373-409, 499-511.  store (n_store, Cd, S): device-resident
+ * descriptor sets [fea ; xyz]; ids (m) int32 slots of the key-frames; poses (m,16) their SE3_pred, row-major;
+ * center (16) the centring SE3 or NULL (identity).  tile (Cd, m*S):
+ *   tile[:, i*S:(i+1)*S] = [ fea_i ; Rc^T ((R_i xyz_i + t_i) - tc) ]   -- the `dst` of dpm_registration_forward. */
+int dpm_map_tile_f32(const float *store, int n_store, int Cd, int S, const int32_t *ids, const float *poses,
+                     const float *center, int m, float *tile, dpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,7 @@
 """GPU parity of the decoder (registration / loop detection through the C-ABI) vs the oracle.
 Bar: R, T, conf, rmse within 1e-4 relative; same correspondences selected."""
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -170,3 +171,38 @@ def test_loop_detection(cfg, checkpoint, golden_sample):
     got = dec.loop_detection_forward(S.to(DEV), D.to(DEV))
     assert got.shape == (3,) and (got.cpu() - want).abs().max() < TOL
     assert np.abs(got[:2].cpu().numpy() - golden_sample["loop"]).max() < TOL or True
+
+
+def test_map_tile_and_scan_to_map_registration(cfg, checkpoint):
+    """device-resident descriptor store -> map tile (vs oracle, 1e-5 of the coordinate range) ->
+    scan-to-map registration (M = 256 scan descriptors against N = 4 x 256 map descriptors)."""
+    import sys
+    from oracle import maptile_ref
+    from deeppointmap_b200 import Encoder, ops, sequence
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_pin import _map_tile_cases
+    kps, poses, center = _map_tile_cases()
+    store = torch.stack(kps).to(DEV)
+    want = maptile_ref.map_tile(kps, poses, center)
+    got = ops.map_tile(store, [0, 1, 2, 3, 4], torch.stack(poses), center).cpu()
+    assert got.shape == want.shape == (131, 5 * 256)
+    assert torch.equal(got[:128], want[:128])
+    assert float((got[128:] - want[128:]).abs().max()) <= 1e-5 * float(want[128:].abs().max())
+    sub = ops.map_tile(store, [3, 1], torch.stack([poses[3], poses[1]])).cpu()   # any subset / order, no centring
+    assert float((sub - maptile_ref.map_tile([kps[3], kps[1]], [poses[3], poses[1]])).abs().max()) <= 1e-4
+
+    # scan-to-map on real descriptors: 5 scans along a corridor, map = scans 0..3 in the frame of scan 3, query = scan 4
+    enc, dec = Encoder(cfg).eval(), Decoder(cfg).eval()
+    enc.load_state_dict(checkpoint["encoder"], strict=True)
+    dec.load_state_dict(checkpoint["decoder"], strict=True)
+    enc, dec = enc.to(DEV), dec.to(DEV)
+    gt = sequence.trajectory(5)
+    world = sequence.corridor_world(4, length_m=float(gt[-1, 0, 3]), device=DEV)
+    frames = sequence.corridor_frames(world, gt, 16384, seed=5)
+    desc = enc.descriptors(frames, None, coor_scale=cfg.coor_scale)
+    tile = ops.map_tile(desc, [0, 1, 2, 3], gt[:4].float(), gt[3].float())
+    R, T, conf, rmse = dec.registration_forward(desc[4], tile, num_sample=0.5)
+    want_rel = torch.linalg.inv(gt[3]) @ gt[4]                    # scan 4 expressed in the map's (scan 3's) frame
+    assert float((T.flatten().cpu().double() - want_rel[:3, 3]).norm()) < 0.6
+    Rw, Tw, cw, rw = M.registration_forward(checkpoint["decoder"], cfg, desc[4].cpu(), tile.cpu(), 0.5)
+    assert float((R.cpu() - Rw).abs().max()) < 1e-4 and float((T.cpu() - Tw).abs().max()) < 1e-4 * max(1.0, float(Tw.abs().max()))

@@ -279,3 +279,73 @@ def test_frontend_oracle_matches_golden():
     g = np.load(os.path.join(ROOT, "tests", "golden", "frontend.npz"))
     got = frontend_ref.preprocess_bin(g["raw"])
     assert torch.equal(got, torch.from_numpy(g["out"]))
+
+
+# ---- scan-to-map input stage -----------------------------------------------------
+def _map_tile_cases():
+    g = torch.Generator().manual_seed(17)
+    import math
+    kps, poses = [], []
+    for i in range(5):
+        kp = torch.randn(131, 256, generator=g)
+        kp[-3:] = kp[-3:] * 20.0
+        a = 0.1 * i
+        T = torch.eye(4)
+        T[0, 0], T[0, 1], T[1, 0], T[1, 1] = math.cos(a), -math.sin(a), math.sin(a), math.cos(a)
+        T[:3, 3] = torch.tensor([2.0 * i, -0.5 * i, 0.1 * i])
+        kps.append(kp)
+        poses.append(T)
+    c = torch.eye(4)
+    c[0, 0], c[0, 1], c[1, 0], c[1, 1] = math.cos(0.3), -math.sin(0.3), math.sin(0.3), math.cos(0.3)
+    c[:3, 3] = torch.tensor([4.0, 1.0, -0.2])
+    return kps, poses, c
+
+
+@needs_ref
+@pytest.mark.reference
+def test_map_tile_matches_reference_posegraph():
+    """oracle/maptile_ref.py vs PoseGraph.__global_mapping + the centring lines of global_map_query_graph"""
+    import importlib
+    import types
+    from oracle import maptile_ref
+    from ref_infomat import reference_module
+    reference_module()  # leaves the reference's system.modules.utils importable (stub open3d / matplotlib)
+    rw = types.ModuleType("readerwriterlock")
+
+    class _Lock:
+        def acquire(self, blocking=True):
+            return True
+
+        def release(self):
+            pass
+
+    class _RW:
+        def gen_wlock(self):
+            return _Lock()
+
+        def gen_rlock(self):
+            return _Lock()
+
+    rw.rwlock = types.SimpleNamespace(RWLockFair=_RW)
+    saved = sys.modules.get("readerwriterlock")
+    sys.modules["readerwriterlock"] = rw
+    sys.path[:0] = [os.path.join(ROOT, "deeppointmap_b200", "compat"), REF]
+    try:
+        PG = importlib.import_module("system.modules.pose_graph")
+    finally:
+        sys.path.remove(REF)
+        if saved is None:
+            sys.modules.pop("readerwriterlock", None)
+    kps, poses, center = _map_tile_cases()
+    pg = PG.PoseGraph(args=None, agent_id=0, device="cpu")
+    scans = []
+    for i, (kp, T) in enumerate(zip(kps, poses)):
+        sp = PG.ScanPack(timestamp=float(i), agent_id=0, timestep=i, key_points=kp, SE3_pred=T, coor_sys=0)
+        pg.add_vertex(sp)
+        scans.append(sp)
+    tile, tokens = pg._PoseGraph__global_mapping(scans, full_pcd=False)
+    R, t = PG.PoseTool.Rt(center)                                # pose_graph.py:505-507
+    tile[-3:, :] = R.T @ (tile[-3:, :] - t)
+    got = maptile_ref.map_tile(kps, poses, center)
+    assert tokens.tolist() == [i for i in range(5) for _ in range(256)]
+    assert torch.equal(got, tile)
