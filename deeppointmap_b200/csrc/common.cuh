@@ -120,6 +120,10 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
 int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
                     int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st, bool pad = false);
 
+// exact uncapped kNN (knn_points contract) over the grid: 3x3x3 block, then shells until provably complete
+int knn_ring_launch(const GridWs &g, const float4 *q4, int B, int S, const int *qlen32, int K, int64_t *idx64,
+                    int32_t *idx32, float *d2out, cudaStream_t st);
+
 // ---- internal launchers shared between translation units ------------------------------
 // xyz4 buffers are float4 (x,y,z,0) rows.
 int fps_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64,

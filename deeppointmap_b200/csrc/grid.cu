@@ -600,6 +600,178 @@ knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// plain (uncapped) kNN over the grid: the 3x3x3 block first, then cubic shells of cells until the K-th
+// distance found is provably final -- every point not yet scanned lies beyond one of the block's faces, so
+// it is at least as far as the nearest face that still has cells behind it.  Same (d2, index) order and
+// the same buffered 32-at-a-time merge as knn_grid_kernel; pytorch3d knn_points contract (ascending,
+// idx / d2 zero-padded when the cloud has fewer than K points).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KG_T)
+knn_ring_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted, int npad,
+                const int *__restrict__ cell_start, const GridDesc *__restrict__ desc, int S,
+                const int *__restrict__ qlen32, int K, int64_t *__restrict__ idx64, int32_t *__restrict__ idx32,
+                float *__restrict__ d2out) {
+    __shared__ float sbd[KG_T / 32][64];
+    __shared__ int sbi[KG_T / 32][64];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (KG_T / 32) + (threadIdx.x >> 5);
+    if (s >= S) return;  // warp-uniform
+    const GridDesc d = desc[b];
+    const int qlen = qlen32 ? min(qlen32[b], S) : S;
+    const size_t o = ((size_t)b * S + s) * K;
+    const float INF = __int_as_float(0x7f800000);
+    float ld = INF;
+    int li = 0x7fffffff;
+    if (s < qlen && d.nvalid > 0) {
+        const float4 c = q4[(size_t)b * S + s];
+        const float4 *P = sorted + (size_t)b * npad;
+        const int *cs = cell_start + (size_t)b * (GRID_MAXCELL + 1);
+        const int cx = cell_coord_free(c.x, d.ox, d.inv_h, d.gx), cy = cell_coord_free(c.y, d.oy, d.inv_h, d.gy),
+                  cz = cell_coord_free(c.z, d.oz, d.inv_h, d.gz);
+        float thrd = INF;
+        int thri = 0x7fffffff;
+        float *bd = sbd[threadIdx.x >> 5];
+        int *bi = sbi[threadIdx.x >> 5];
+        int fill = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        auto flush = [&](float cd, int ci) {
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, cd, j);
+                    const int oi = __shfl_xor_sync(0xffffffffu, ci, j);
+                    const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+                    const bool less = od < cd || (od == cd && oi < ci);
+                    if (keep_min == less) { cd = od; ci = oi; }
+                }
+            }
+            const float rd = __shfl_sync(0xffffffffu, cd, 31 - lane);
+            const int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+            if (rd < ld || (rd == ld && ri < li)) { ld = rd; li = ri; }
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, ld, j);
+                const int oi = __shfl_xor_sync(0xffffffffu, li, j);
+                const bool keep_min = (lane & j) == 0;
+                const bool less = od < ld || (od == ld && oi < li);
+                if (keep_min == less) { ld = od; li = oi; }
+            }
+            if (lane >= K) { ld = INF; li = 0x7fffffff; }
+            const float kd = __shfl_sync(0xffffffffu, ld, K - 1);
+            const int ki = __shfl_sync(0xffffffffu, li, K - 1);
+            if (kd < INF) { thrd = kd; thri = ki; }
+        };
+        auto scan = [&](int st, int en) {  // warp-uniform range of the sorted array
+            for (int i0 = st; i0 < en; i0 += 32) {
+                const int i = i0 + lane;
+                float dd = INF;
+                int gi = 0x7fffffff;
+                if (i < en) {
+                    const float4 p = P[i];
+                    dd = d2_exact(c.x, c.y, c.z, p.x, p.y, p.z);
+                    gi = __float_as_int(p.w);
+                }
+                const bool pass = dd < thrd || (dd == thrd && gi < thri);
+                const unsigned cm = __ballot_sync(0xffffffffu, pass);
+                if (cm) {
+                    if (pass) {
+                        const int slot = fill + __popc(cm & lt);
+                        bd[slot] = dd;
+                        bi[slot] = gi;
+                    }
+                    fill += __popc(cm);
+                    if (fill >= 32) {
+                        __syncwarp();
+                        const float cd = bd[lane];
+                        const int ci = bi[lane];
+                        const float td = bd[32 + lane];
+                        const int ti = bi[32 + lane];
+                        __syncwarp();
+                        fill -= 32;
+                        if (lane < fill) { bd[lane] = td; bi[lane] = ti; }
+                        flush(cd, ci);
+                    }
+                }
+            }
+        };
+        const int gmax = max(d.gx, max(d.gy, d.gz));
+        for (int R = 1;; ++R) {
+            // ---- cells of shell R (R = 1: the whole 3x3x3 block): rows (dy, dz), one or two x-segments each ----
+            const int side = 2 * R + 1;
+            for (int t0 = 0; t0 < side * side; t0 += 32) {
+                const int t = t0 + lane;
+                int s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+                if (t < side * side) {
+                    const int dy = t % side - R, dz = t / side - R;
+                    const int yy = cy + dy, zz = cz + dz;
+                    if (yy >= 0 && yy < d.gy && zz >= 0 && zz < d.gz) {
+                        const int row = (zz * d.gy + yy) * d.gx;
+                        if (R == 1 || abs(dy) == R || abs(dz) == R) {
+                            const int x0 = max(cx - R, 0), x1 = min(cx + R, d.gx - 1);
+                            if (x0 <= x1) { s0 = cs[row + x0]; e0 = cs[row + x1 + 1]; }
+                        } else {
+                            const int xa = cx - R, xb = cx + R;
+                            if (xa >= 0 && xa < d.gx) { s0 = cs[row + xa]; e0 = cs[row + xa + 1]; }
+                            if (xb >= 0 && xb < d.gx) { s1 = cs[row + xb]; e1 = cs[row + xb + 1]; }
+                        }
+                    }
+                }
+                unsigned nz = __ballot_sync(0xffffffffu, e0 > s0 || e1 > s1);
+                while (nz) {
+                    const int src = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const int a0 = __shfl_sync(0xffffffffu, s0, src), b0 = __shfl_sync(0xffffffffu, e0, src);
+                    const int a1 = __shfl_sync(0xffffffffu, s1, src), b1 = __shfl_sync(0xffffffffu, e1, src);
+                    scan(a0, b0);
+                    scan(a1, b1);
+                }
+            }
+            if (fill > 0) {
+                __syncwarp();
+                flush(lane < fill ? bd[lane] : INF, lane < fill ? bi[lane] : 0x7fffffff);
+                fill = 0;
+            }
+            // ---- done?  every unscanned point is beyond a face of the block that still has cells behind it ----
+            const bool cover = cx - R <= 0 && cx + R >= d.gx - 1 && cy - R <= 0 && cy + R >= d.gy - 1 && cz - R <= 0 &&
+                               cz + R >= d.gz - 1;
+            if (cover || R > gmax + 3) break;
+            float gap = INF;
+            if (cx - R > 0) gap = fminf(gap, c.x - (d.ox + (float)(cx - R) * d.h));
+            if (cx + R < d.gx - 1) gap = fminf(gap, (d.ox + (float)(cx + R + 1) * d.h) - c.x);
+            if (cy - R > 0) gap = fminf(gap, c.y - (d.oy + (float)(cy - R) * d.h));
+            if (cy + R < d.gy - 1) gap = fminf(gap, (d.oy + (float)(cy + R + 1) * d.h) - c.y);
+            if (cz - R > 0) gap = fminf(gap, c.z - (d.oz + (float)(cz - R) * d.h));
+            if (cz + R < d.gz - 1) gap = fminf(gap, (d.oz + (float)(cz + R + 1) * d.h) - c.z);
+            // the cell of a point is floor((p - o) * inv_h) in fp32: leave a margin for that rounding
+            gap -= 1e-4f * (d.h + fabsf(c.x - d.ox) + fabsf(c.y - d.oy) + fabsf(c.z - d.oz));
+            const float kd = __shfl_sync(0xffffffffu, ld, min(K, d.nvalid) - 1);
+            if (gap > 0.f && kd <= gap * gap) break;
+        }
+    }
+    const unsigned kmask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+    const int count = __popc(__ballot_sync(0xffffffffu, ld < INF) & kmask);
+    if (lane < K) {
+        const int oi = lane < count ? li : 0;
+        if (idx64) idx64[o + lane] = (int64_t)oi;
+        if (idx32) idx32[o + lane] = oi;
+        if (d2out) d2out[o + lane] = lane < count ? ld : 0.f;
+    }
+}
+
+int knn_ring_launch(const GridWs &g, const float4 *q4, int B, int S, const int *qlen32, int K, int64_t *idx64,
+                    int32_t *idx32, float *d2out, cudaStream_t st) {
+    if (B <= 0 || S <= 0) return fail(DPM_ERR_SHAPE, "knn: bad shape B=%d S=%d", B, S);
+    if (K <= 0 || K > 32) return fail(DPM_ERR_UNSUPPORTED, "knn: K=%d not in 1..32", K);
+    prof_note(S, 0);
+    dim3 grid((S + KG_T / 32 - 1) / (KG_T / 32), B, 1);
+    knn_ring_kernel<<<grid, KG_T, 0, st>>>(q4, g.sorted, g.npad, g.cell_start, g.desc, S, qlen32, K, idx64, idx32, d2out);
+    DPM_CHECK_LAUNCH("knn", st);
+    return DPM_OK;
+}
+
 int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
                     int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st, bool pad) {
     if (B <= 0 || S <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "knn: bad shape B=%d S=%d N=%d", B, S, N);

@@ -14,6 +14,7 @@
 // and the rare insertion is a ballot + shuffle-up.  For the hybrid query the list is
 // additionally capped at the radius, which removes the warm-up insertions.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -314,6 +315,14 @@ static int knn_common(const float *p1, int D1, const float *p2, int D2, int B, i
         if (!grid_ws_carve(a, B, N, &g)) return fail(DPM_ERR_WORKSPACE, "knn: workspace too small");
         DPM_TRY(grid_build_launch(p4, B, N, lengths2 ? l2 : nullptr, 1.001f * sqrtf(r2), g, st));
         return knn_grid_launch(g, q4, p4, B, S, N, lengths1 ? l1 : nullptr, K, r2, idx_out, nullptr, st);
+    }
+    static const bool brute = getenv("DPM_KNN_BRUTE") != nullptr;  // developer A/B switch
+    if (which == 0 && N >= GRID_MIN_N && N <= GRID_MAX_N && K <= 32 && !brute) {
+        // plain kNN on a large cloud: cell grid + shells until the K-th distance is provably final
+        GridWs g;
+        if (!grid_ws_carve(a, B, N, &g)) return fail(DPM_ERR_WORKSPACE, "knn: workspace too small");
+        DPM_TRY(grid_build_launch(p4, B, N, lengths2 ? l2 : nullptr, 0.f, g, st));
+        return knn_ring_launch(g, q4, B, S, lengths1 ? l1 : nullptr, K, idx_out, nullptr, d2_out, st);
     }
     return knn_launch(q4, p4, B, S, N, lengths1 ? l1 : nullptr, lengths2 ? l2 : nullptr, K, r2,
                       which == 1 ? KNN_MODE_HYBRID : KNN_MODE_KNN, idx_out, nullptr, d2_out, st);

@@ -81,6 +81,30 @@ def test_knn_lengths_and_zero_padding():
     assert (got.idx[1, :, 7:] == 0).all() and (got.dists[1, :, 7:] == 0).all()
 
 
+@pytest.mark.parametrize("n,k", [(46000, 12), (46000, 18), (2048, 32), (30000, 1)])
+def test_knn_grid_shells_self_and_foreign_queries(n, k):
+    """plain kNN on a large cloud takes the cell-grid + shell-expansion path: self queries (OutlierFilter /
+    LowPassFilter, dataloader/transforms.py:236-289), queries far outside the cloud, ragged lengths, a cloud with
+    fewer than K valid points, lattice ties -- all bit-exact (indices and distances) against the C oracle."""
+    cloud = _cloud("kitti", n, n) * 60.0  # metres, like the filters see it
+    far = torch.tensor([[500.0, -300.0, 40.0], [-1e4, 0.0, 0.0], [0.0, 0.0, 1e3], [59.9, 59.9, 5.0]])
+    lattice = (torch.stack(torch.meshgrid(torch.arange(16.0), torch.arange(16.0), torch.arange(8.0), indexing="ij"), -1)
+               .reshape(-1, 3) * 0.5)
+    p2 = torch.stack([cloud, torch.cat([lattice, cloud[: n - lattice.shape[0]] + 100.0])])
+    q = torch.stack([torch.cat([cloud[:1500], far, cloud[-500:] + 0.3]), torch.cat([lattice[:1500] + 0.25, far, lattice[:500]])])
+    l2 = torch.tensor([n, min(n, lattice.shape[0] + 7)])
+    l1 = torch.tensor([q.shape[1], 1700])
+    wd, wi = IO.knn(q, p2, l2, k)
+    got = ops.knn_points(q.to(DEV), p2.to(DEV), lengths1=l1.to(DEV), lengths2=l2.to(DEV), K=k)
+    gi, gd = got.idx.cpu(), got.dists.cpu()
+    assert torch.equal(gi[0], wi[0]) and torch.equal(gd[0], wd[0])
+    assert torch.equal(gi[1, :1700], wi[1, :1700]) and torch.equal(gd[1, :1700], wd[1, :1700])
+    assert (gi[1, 1700:] == 0).all() and (gd[1, 1700:] == 0).all()          # queries past lengths1: zeros
+    tiny = ops.knn_points(q[:1, :64].to(DEV), p2[:1].to(DEV), lengths2=torch.tensor([5], device=DEV), K=k)
+    wd5, wi5 = IO.knn(q[:1, :64], p2[:1], torch.tensor([5]), k)
+    assert torch.equal(tiny.idx.cpu(), wi5) and torch.equal(tiny.dists.cpu(), wd5)  # fewer than K points: zero padded
+
+
 def test_knn_ties_lower_index_first():
     p2 = torch.zeros(1, 100, 3)
     p2[0, 50:] = 2.0
