@@ -168,11 +168,17 @@ def information_matrix(pointcloud_1: torch.Tensor, pointcloud_2: torch.Tensor, S
 
 
 def preprocess_frame(raw: torch.Tensor, voxel_size: float = 0.3, min_dis: float = 1.0, max_dis: float = 60.0,
-                     ratio: float = 60.0, max_voxels: int = 1 << 26) -> torch.Tensor:
+                     ratio: float = 60.0, max_voxels: int = 1 << 26, outlier=None) -> torch.Tensor:
     """Raw frame -> encoder input on the device: BinReader's NaN-row drop, VoxelSample(voxel_size, 'first'),
-    DistanceSample(min_dis, max_dis), CoordinatesNormalization(ratio) (dataloader/heads/bin.py:16-17,
-    dataloader/transforms.py:331-356, 387-407).  raw (N, C>=3) CUDA fp32 rows (a KITTI .bin is (N,4)) ->
-    (3, n) fp32, points in the reference's order (ascending voxel id).  One host sync (n is data dependent)."""
+    DistanceSample(min_dis, max_dis), [OutlierFilter(*outlier), e.g. outlier=(10, 3.0) as in the shipped YAML],
+    CoordinatesNormalization(ratio) (dataloader/heads/bin.py:16-17, dataloader/transforms.py:230-246, 331-356,
+    387-407).  raw (N, C>=3) CUDA fp32 rows (a KITTI .bin is (N,4)) -> (3, n) fp32, points in the reference's
+    order (ascending voxel id).  One host sync per data-dependent size."""
+    if outlier is not None:
+        pts = preprocess_frame(raw, voxel_size, min_dis, max_dis, 1.0, max_voxels)        # metres (x / 1.0 is exact)
+        # pcd.xyz /= ratio as an IEEE division inside the filter's emit pass (torch's CUDA `/ scalar` multiplies by
+        # the reciprocal, which is 1 ulp off the reference's CPU arithmetic)
+        return outlier_filter(pts.T.contiguous(), int(outlier[0]), float(outlier[1]), out_divisor=float(ratio)).T.contiguous()
     _C.require_cuda(raw)
     if raw.dim() != 2 or raw.shape[1] < 3:
         raise ValueError("raw must be (N, C>=3)")
@@ -220,3 +226,34 @@ def map_tile(store: torch.Tensor, ids, poses: torch.Tensor, center: Optional[tor
         _C.check(_C.lib().dpm_map_tile_f32(st.data_ptr(), n, Cd, S, idt.data_ptr(), P.data_ptr(), _C.ptr(C), m,
                                            tile.data_ptr(), _C.stream_ptr()), "map_tile")
     return tile
+
+
+def outlier_filter(rows: torch.Tensor, nb_neighbors: int = 10, std_ratio: float = 3.0, return_mask: bool = False,
+                   out_divisor: float = 1.0):
+    """OutlierFilter, the reference's CUDA branch (dataloader/transforms.py:230-246), in one native call:
+    rows (N, C>=3) CUDA fp32 -> (n, 3) rows kept (original order, IEEE-divided by out_divisor)
+    [, (N,) bool mask].  One host sync (n)."""
+    _C.require_cuda(rows)
+    if rows.dim() != 2 or rows.shape[1] < 3:
+        raise ValueError("rows must be (N, C>=3)")
+    r = _f32c(rows)
+    n, stride = r.shape
+    dev = r.device
+    if n == 0:
+        e = torch.empty((0, 3), dtype=torch.float32, device=dev)
+        return (e, torch.empty((0,), dtype=torch.bool, device=dev)) if return_mask else e
+    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((n,), dtype=torch.bool, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    lib = _C.lib()
+    nb = lib.dpm_outlier_filter_workspace_bytes(n, int(nb_neighbors))
+    if nb == 0:
+        raise NotImplementedError("nb_neighbors must be in 1..31")
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        _C.check(lib.dpm_outlier_filter_f32(r.data_ptr(), n, stride, int(nb_neighbors), float(std_ratio), float(out_divisor),
+                                            out.data_ptr(),
+                                            mask.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr()),
+                 "outlier_filter")
+    kept = out[:int(cnt.item())]
+    return (kept, mask) if return_mask else kept

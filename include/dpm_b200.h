@@ -274,6 +274,17 @@ int dpm_frontend_f32(const float *raw, int N, int stride, float voxel_size, floa
 int dpm_map_tile_f32(const float *store, int n_store, int Cd, int S, const int32_t *ids, const float *poses,
                      const float *center, int m, float *tile, dpm_stream_t stream);
 
+/* OutlierFilter, the reference's CUDA branch (dataloader/transforms.py:230-246): rows (N x stride floats, xyz
+ * first) -> the rows whose mean distance to their nb_neighbors nearest neighbours is <= mean + std_ratio * std
+ * of that statistic over the cloud, in their original order, divided by out_divisor (1 = as they are; the
+ * CoordinatesNormalization ratio when the filter is the last step before it).  out_rows: room for N x 3 floats;
+ * mask (N bytes, optional) the keep flags; count (device int32) the number of survivors.  nb_neighbors <= 31.
+ * No host sync. */
+size_t dpm_outlier_filter_workspace_bytes(int N, int nb_neighbors);
+int dpm_outlier_filter_f32(const float *rows, int N, int stride, int nb_neighbors, float std_ratio,
+                           float out_divisor, float *out_rows, uint8_t *mask, int32_t *count, void *workspace,
+                           size_t ws_bytes, dpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,3 +63,38 @@ def test_frontend_feeds_the_encoder(cfg):
     assert pts.shape[0] == 3 and pts.shape[1] > 4096 and float(pts.norm(dim=0).max()) <= 1.0 + 1e-6
     coor, fea, pad = enc(pts[None], torch.zeros(1, pts.shape[1], dtype=torch.bool, device=DEV))
     assert coor.shape == (1, 3, 256) and fea.shape == (1, 128, 256) and not bool(pad.any())
+
+
+@pytest.mark.parametrize("n", [46000, 6000, 300])
+def test_outlier_filter_vs_oracle(n):
+    """The kept set equals the oracle's except, at most, for points whose statistic lies within 1e-5 (relative) of
+    the threshold: the reference sums the global mean / std in fp32 in a build-dependent order, we in fp64."""
+    from oracle import outlier_ref
+    raw = _raw_frame(n + 1, n)
+    xyz = torch.from_numpy(raw[~np.isnan(raw).any(1), :3]).contiguous()
+    g = torch.Generator().manual_seed(n)
+    xyz[torch.randint(0, xyz.shape[0], (20,), generator=g)] += 30.0 * torch.randn(20, 3, generator=g)   # real outliers
+    kept_w, mask_w, stat, thr = outlier_ref.outlier_filter(xyz, 10, 3.0)
+    kept, mask = ops.outlier_filter(xyz.to(DEV), 10, 3.0, return_mask=True)
+    mask = mask.cpu()
+    diff = mask != mask_w
+    assert int((~mask_w).sum()) >= 3                                   # the filter has work to do
+    assert bool(((stat[diff] - thr).abs() <= 1e-5 * abs(thr)).all()), (int(diff.sum()), thr)
+    assert int(diff.sum()) <= 2
+    assert torch.equal(kept.cpu(), xyz[mask])                          # survivors, original order
+    if not bool(diff.any()):
+        assert torch.equal(kept.cpu(), kept_w)
+
+
+def test_frontend_with_outlier_filter_is_the_yaml_chain():
+    """VoxelSample -> DistanceSample -> OutlierFilter(10, 3.0) -> CoordinatesNormalization, the shipped YAML's chain
+    minus the open3d LowPassFilter (configs/infer/DeepPointMap_B_Main_SemanticKITTI.yaml:21-29)."""
+    from oracle import outlier_ref
+    raw = _raw_frame(77, 100000)
+    metres = (frontend_ref.preprocess_bin(raw, ratio=1.0)).T.contiguous()
+    kept_w, mask_w, stat, thr = outlier_ref.outlier_filter(metres, 10, 3.0)
+    want = (kept_w / 60.0).T.contiguous()
+    got = ops.preprocess_frame(torch.from_numpy(raw).to(DEV), outlier=(10, 3.0)).cpu()
+    assert abs(got.shape[1] - want.shape[1]) <= 2
+    if got.shape == want.shape:
+        assert torch.equal(got, want)

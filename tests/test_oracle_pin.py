@@ -349,3 +349,23 @@ def test_map_tile_matches_reference_posegraph():
     got = maptile_ref.map_tile(kps, poses, center)
     assert tokens.tolist() == [i for i in range(5) for _ in range(256)]
     assert torch.equal(got, tile)
+
+
+# ---- OutlierFilter (second half) ---------------------------------------------------
+@needs_ref
+@pytest.mark.reference
+def test_outlier_filter_matches_reference():
+    """oracle/outlier_ref.py vs the reference's OutlierFilter class, CUDA branch (transforms.py:236-246) forced
+    onto CPU tensors: `pcd.device` reads 'cuda:fake', knn_points is a plain-torch stand-in."""
+    from oracle import frontend_ref, outlier_ref
+    from ref_infomat import _cpu_knn_points
+    RT = _reference_transforms()
+    RT.has_t3d, RT.knn_points = True, _cpu_knn_points
+    raw = np.fromfile(f"{REF}/data/sample/seq06/velodyne/000005.bin", dtype=np.float32).reshape(-1, 4)
+    xyz = (frontend_ref.preprocess_bin(raw) * 60.0).T.contiguous()[:6000]     # metres, after voxel + distance sampling
+    pcd = RT.PointCloud(xyz.numpy().copy())
+    pcd.device = "cuda:fake"
+    out = RT.OutlierFilter(nb_neighbors=10, std_ratio=3.0)(pcd)
+    kept, mask, stat, thr = outlier_ref.outlier_filter(xyz, 10, 3.0)
+    assert 0 < int((~mask).sum()) < 600
+    assert torch.equal(out.xyz, kept)
