@@ -409,6 +409,35 @@ def main():
             ms1 = b0.elapsed_time(b1) / n1
             batch1 = {"frames_per_s": 1e3 / ms1, "ms_per_frame": ms1, "streams": 1, "frames_per_step": 1,
                       "note": "latency-bound: 4095 + 1023 + 255 + 63 + 15 sequential FPS picks per frame"}
+            # the same step captured once into a CUDA graph and replayed (the calls never sync or allocate)
+            try:
+                gin = one[0].clone()
+                cs = torch.cuda.Stream(device=dev)
+                cs.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cs):
+                    enc.descriptors(gin, None, coor_scale=cfg.coor_scale, out=db1[1:])
+                    dec.registration_forward_batch(db1[:1], db1[1:], 0.5)
+                torch.cuda.current_stream().wait_stream(cs)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=cs):
+                    enc.descriptors(gin, None, coor_scale=cfg.coor_scale, out=db1[1:])
+                    gres, _ = dec.registration_forward_batch(db1[:1], db1[1:], 0.5)
+                    db1[0].copy_(db1[1])
+                for i in range(3):
+                    gin.copy_(one[i % len(one)])
+                    graph.replay()
+                torch.cuda.synchronize()
+                b0.record()
+                for i in range(n1):
+                    gin.copy_(one[(3 + i) % len(one)])
+                    graph.replay()
+                b1.record()
+                torch.cuda.synchronize()
+                batch1["cuda_graph_ms_per_frame"] = b0.elapsed_time(b1) / n1
+            except Exception as e:  # noqa: BLE001 -- report, the eager figure stands
+                batch1["cuda_graph_ms_per_frame"] = None
+                batch1["cuda_graph_error"] = str(e)[:200]
 
         # ---- per-kernel profile pass (CUDA events after every launch, same stream) ---------
         prof_steps = 3

@@ -54,3 +54,38 @@ def test_concurrent_threads_match_sequential(cfg, checkpoint):
     # and repeated calls are deterministic
     for t in range(4):
         assert torch.equal(seq[t][0][0], seq[t][2][0]) and torch.equal(seq[t][0][1], seq[t][2][1])
+
+
+def test_step_is_cuda_graph_capturable(cfg, checkpoint):
+    """No host sync, no allocation and no default-stream work inside the C-ABI calls: one frame's encoder (with its
+    forked sampling chain) + registration can be captured into a CUDA graph and replayed on new inputs."""
+    enc, dec = Encoder(cfg).eval(), Decoder(cfg).eval()
+    enc.load_state_dict(checkpoint["encoder"], strict=True)
+    dec.load_state_dict(checkpoint["decoder"], strict=True)
+    enc, dec = enc.to(DEV), dec.to(DEV)
+    a = torch.stack([data.kitti_shape_cloud(1, 16384), data.kitti_shape_cloud(2, 16384)]).to(DEV)
+    b = torch.stack([data.kitti_shape_cloud(3, 16384), data.kitti_shape_cloud(4, 16384)]).to(DEV)
+    static_in = a.clone()
+
+    def step(x):
+        desc = enc.descriptors(x, None, coor_scale=cfg.coor_scale)
+        res, conf = dec.registration_forward_batch(desc[:1], desc[1:], 0.5)
+        return desc, res
+
+    with torch.no_grad():
+        want_a = [t.clone() for t in step(a)]
+        want_b = [t.clone() for t in step(b)]
+        side = torch.cuda.Stream(device=DEV)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up on the capture stream: workspaces / forked streams exist
+            step(static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            out = step(static_in)
+        for inp, want in ((a, want_a), (b, want_b), (a, want_a)):
+            static_in.copy_(inp)
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out[0], want[0]) and torch.equal(out[1], want[1])
