@@ -128,6 +128,10 @@ static Fork *fork_for(cudaStream_t st) {
     return &f;
 }
 
+// a level gets a cell grid for its neighbour queries from this many points on (its FPS switches to the
+// grid kernel at GRID_MIN_N)
+constexpr int ENC_KNN_GRID_MIN_N = 1024;
+
 struct Level {
     float4 *xyz;
     float *fea;
@@ -218,7 +222,7 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
     float4 *comp = fold_stem ? a.get<float4>((size_t)2 * d->width) : nullptr;
     l0.len = a.get<int>(B);
     l0.pad = nullptr;  // level-0 padding is the caller's tensor
-    l0.has_grid = N >= GRID_MIN_N && N <= GRID_MAX_N;
+    l0.has_grid = N >= ENC_KNN_GRID_MIN_N && N <= GRID_MAX_N;
     if (l0.has_grid) grid_ws_carve(a, B, N, &l0.grid);
     const float *W0 = W(), *b0 = W();
     if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
@@ -254,11 +258,11 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
             dst.pad = a.get<uint8_t>((size_t)B * S);
             dst.len = a.get<int>(B);
             dst.fea = a.get<float>((size_t)B * S * Cout);
-            dst.has_grid = S >= GRID_MIN_N && S <= GRID_MAX_N && (d->n_blocks[i] > 1 || i + 1 < d->n_stages);
+            dst.has_grid = S >= ENC_KNN_GRID_MIN_N && S <= GRID_MAX_N && (d->n_blocks[i] > 1 || i + 1 < d->n_stages);
             if (dst.has_grid) grid_ws_carve(a, B, S, &dst.grid);
             if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "encoder: workspace too small");
             if (!dry) {
-                if (src.has_grid)
+                if (src.has_grid && src.n >= GRID_MIN_N)  // the pruned FPS only pays from ~2048 points on
                     DPM_TRY(fps_grid_launch(src.grid, src.xyz, B, src.n, S, trace_fps ? trace_fps + fps_off : nullptr, nullptr,
                                             dst.xyz, dst.pad, dst.len, sst));
                 else
