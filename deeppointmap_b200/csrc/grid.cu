@@ -230,6 +230,7 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 // Keeping a 4096-point level entirely in shared memory (no L2 round trip at all) does not change its
 // 0.75 us per pick: what bounds a pick is the ~100-instruction dependent chain of tests and three levels of
 // arg-max (64 points -> bucket, 32 buckets -> warp, 32 warps -> block), not where the points live.
+// Letting untouched warps republish their previous record instead of recomputing it: 4.89 -> 5.36 ms.
 // ---------------------------------------------------------------------------------------
 template <int PPL, int T, int BPT, int D>
 __global__ void __launch_bounds__(T, 1)
