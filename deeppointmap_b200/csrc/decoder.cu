@@ -75,7 +75,7 @@ int posenc_launch(const float *xyz, int ldx, const float *dim_t, int npf, float 
 // A fragments of P V once the 8 keys of a k-step are taken in the order (0,2,4,6,1,3,5,7), which
 // only changes which V rows are loaded into the B fragment.
 // ---------------------------------------------------------------------------------------
-constexpr int AT_BQ = 128, AT_BK = 64, AT_LD = 36;
+constexpr int AT_BQ = 128, AT_BK = 64, AT_LD = 36, AT_T = AT_BQ * 2;  // 16 query rows per warp; 64 / 256 queries per CTA measured 10 % slower
 
 __device__ __forceinline__ unsigned tf32_bits(float x) {
     unsigned r;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], const unsigned (&
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(AT_T, 512 / AT_T)
 attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__ Kp, int ldk,
                     const float *__restrict__ Vp, int ldv, float *__restrict__ O, int ldo, const int *__restrict__ prob,
                     int M, int N, int mode) {
@@ -137,7 +137,7 @@ attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restric
 
     for (int c0 = 0; c0 < Lk; c0 += AT_BK) {
         __syncthreads();
-        for (int e = tid; e < AT_BK * 8; e += 256) {
+        for (int e = tid; e < AT_BK * 8; e += AT_T) {
             const int key = e >> 3, part = e & 7;
             float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
             if (c0 + key < Lk) {
@@ -246,7 +246,7 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
     if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
     dim3 grid((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
-    attention_tc_kernel<<<grid, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
+    attention_tc_kernel<<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
     DPM_CHECK_LAUNCH("attention", st);
     return DPM_OK;
 }
