@@ -96,6 +96,8 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thr = None
         try:
+            if index < 0:
+                raise RuntimeError("sampling disabled on this rank")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -126,7 +128,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop.wait(0.004)
+            self._stop.wait(0.008)
 
     def __enter__(self):
         if self.nv is not None:
@@ -328,7 +330,7 @@ def main():
         barrier()
         # ---- timed region: K steps, CUDA events on the launching streams ---------------------
         _C.launch_count_reset()
-        with ClockSampler(local) as clk:
+        with ClockSampler(local if rank == 0 else -1) as clk:  # rank 0 reports the clocks; NVML polling stays off the other ranks
             t_wall = time.perf_counter()
             ev0, ev1 = run_steps(K, W, lambda i, q: step(dev_pool[i % nslots], q))
             barrier()
