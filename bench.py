@@ -288,6 +288,7 @@ def main():
     gathered = [torch.empty((world * F, _C.REG_STRIDE), dtype=torch.float32, device=dev) if world > 1 else None
                 for _ in range(NS)]
     k_pairs = dec.num_pairs(0.5, S, S)
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step(pts, q=0):
         """device-resident step of sequence q (on the current stream): F frames -> F descriptors -> F poses"""
@@ -296,7 +297,14 @@ def main():
         result, conf = dec.registration_forward_batch(db[:F], db[1:], 0.5)
         db[0].copy_(db[F])
         if world > 1:
-            dist.all_gather_into_tensor(gathered[q], result)
+            # the pose all-gather (64 B per frame) runs on its own stream behind this step's event: the compute
+            # streams never wait for the other ranks, so one slow rank does not stall the next step of the rest
+            done = torch.cuda.Event()
+            done.record()
+            comm.wait_event(done)
+            result.record_stream(comm)
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(gathered[q], result)
         return result, conf
 
     def barrier():
@@ -317,7 +325,7 @@ def main():
             q = i % NS
             with torch.cuda.stream(streams[q]):
                 fn(first + i, q)
-        for st in streams:
+        for st in streams + ([comm] if comm is not None else []):  # the gathered poses are part of the job
             e = torch.cuda.Event()
             e.record(st)
             cur.wait_event(e)
@@ -327,10 +335,13 @@ def main():
     with torch.no_grad():
         # every stream is warmed (its workspace allocated) before the timed region; one extra step staggers them
         run_steps(max(W, NS) + (1 if NS > 1 else 0), 0, lambda i, q: step(dev_pool[i % nslots], q))
+        # rank 0 reports the clocks (NVML polling stays off the other ranks); nvmlInit happens BEFORE the barrier so that
+        # no rank enters the timed region late and makes the others wait in their first collective
+        clk_obj = ClockSampler(local if rank == 0 else -1)
         barrier()
         # ---- timed region: K steps, CUDA events on the launching streams ---------------------
         _C.launch_count_reset()
-        with ClockSampler(local if rank == 0 else -1) as clk:  # rank 0 reports the clocks; NVML polling stays off the other ranks
+        with clk_obj as clk:
             t_wall = time.perf_counter()
             ev0, ev1 = run_steps(K, W, lambda i, q: step(dev_pool[i % nslots], q))
             barrier()
