@@ -46,6 +46,8 @@ _SIGS = {
     "dpm_prof_end": ([ctypes.c_char_p, _sz], _i),
     "dpm_fps_f32": ([_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_fps_workspace_bytes": ([_i, _i, _i, _i], _sz),
+    "dpm_set_fps_mode": ([_i], None),
+    "dpm_fps_cluster_capacity": ([], _i),
     "dpm_knn_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_knn_radius_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _f, _vp, _vp, _sz, _vp], _i),
     "dpm_ball_query_f32": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp], _i),

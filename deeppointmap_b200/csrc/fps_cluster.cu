@@ -1,0 +1,614 @@
+// fps_cluster.cu -- the LATENCY variants of farthest point sampling: one cloud spread over a cluster of
+// 8 CTAs x 4 warps (8 SMs), bit-exact with Sampler.fps (network/encoder/utils.py:209-270) like every other
+// FPS kernel here.
+//
+// Why: the one-CTA-per-cloud kernel of grid.cu keeps 32 warps on ONE SM, so the ~100-instruction chain of a
+// pick is issued 8 warps deep per scheduler (issue-active 50 %, 1.2 us per pick, 32 of 148 SMs busy for a
+// batch of 32).  That is the right shape when other streams fill the rest of the chip; for a single frame
+// (pipeline/infer.py runs batch 1) it leaves 147 SMs idle behind a 4095-pick chain.  Here every warp has a
+// scheduler to itself, the cloud is resident in the cluster's shared memory (65 536 points x 20 B = 1.25 MB
+// over 8 x 160 KB), and the per-pick arg-max crosses the cluster without a cluster barrier:
+//
+//   * every warp reduces its own candidate (two REDUX + ballot), then 16 lanes push the 32-byte record
+//     (value bits, ~index, xyz) into the record table of EVERY CTA with st.async -- the store itself
+//     signals the destination's mbarrier (complete_tx), so there is no separate arrive and no
+//     barrier.cluster per pick;
+//   * every warp waits on its own CTA's mbarrier (32 records x 32 B), loads one record per lane and
+//     reduces them -- all 32 warps reach the same winner without another exchange;
+//   * records and mbarriers are double-buffered by pick parity; a warp can only publish pick k+2 after
+//     it has seen every warp's record of pick k+1, which those warps sent after reading pick k -- so two
+//     buffers are enough and the mbarrier of pick k is re-armed (expect_tx) right after its wait.
+//
+//   fps_grid_cluster_kernel  : the bucket-pruned FPS of grid.cu (same buckets, same arithmetic), buckets
+//                              dealt over the 32 warps of the cluster, tiles in shared memory (N <= 65 536)
+//                              or left in L2 (larger clouds).
+//   fps_brute_cluster_kernel : clouds of <= 8192 points: every point in registers (<= 8 per thread), all
+//                              min-distances updated per pick -- cheaper than a box test at that size.
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dpm {
+
+constexpr int FC_CS = 8;                  // CTAs per cloud
+constexpr int FC_WPC = 4;                 // warps per CTA: one per scheduler
+constexpr int FC_T = FC_WPC * 32;
+constexpr int FC_NW = FC_CS * FC_WPC;     // warps per cloud = records per pick (one per lane of the reducing warp)
+static_assert(FC_NW == 32, "the record reduce takes one record per lane");
+constexpr unsigned FC_TX = FC_NW * 32u;   // bytes that complete one pick's mbarrier phase
+
+struct __align__(16) FcShared {
+    uint4 rec[2][FC_NW][2];     // [parity][warp of the cluster][half]: {value bits, ~index, x, y}, {z, -, -, -}
+    uint4 stage[2][FC_WPC][2];  // [parity][warp]: this warp's record, written by its winning lane, pushed out by 16 lanes
+    uint4 win[2][FC_WPC];       // [parity][warp]: the cluster-wide winner {~index, x, y, z} as this warp reduced it
+    uint4 tmp[2][FC_WPC];       // [toggle][warp]: broadcast slot of the bucket-level arg-max
+    unsigned long long bar[2];
+};
+
+// developer build (-DDPM_FC_PROFILE): cycles per phase of a pick, summed over the warps of the cluster
+#ifdef DPM_FC_PROFILE
+__device__ unsigned long long fc_prof[16];
+#define FC_TICK(i)                                               \
+    do {                                                         \
+        const long long _t = clock64();                          \
+        pacc[i] += _t - tprev;                                   \
+        tprev = _t;                                              \
+    } while (0)
+#else
+#define FC_TICK(i) do { } while (0)
+#endif
+
+__device__ __forceinline__ unsigned fc_s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned fc_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void fc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned fc_mapa(unsigned local, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void fc_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// one arrival + `bytes` expected transaction bytes: the phase completes when they have all landed
+__device__ __forceinline__ void fc_mbar_arm(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fc_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 16-byte store into a peer CTA's shared memory that completes 16 transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void fc_st_async16(unsigned raddr, uint4 v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void fc_setup(FcShared &sh, int tid) {
+    if (tid == 0) {
+        fc_mbar_init(fc_s32(&sh.bar[0]), 1);
+        fc_mbar_init(fc_s32(&sh.bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fc_mbar_arm(fc_s32(&sh.bar[0]), FC_TX);
+        fc_mbar_arm(fc_s32(&sh.bar[1]), FC_TX);
+    }
+}
+
+// Warp arg-max of (value bits, tie key) -- both "larger wins" -- with a three-word payload.  One REDUX finds the
+// largest value; the lane that holds it drops {tie key, payload} into a shared-memory slot that every lane reads
+// back (STS + LDS broadcast, ~40 cycles).  Measured alternatives on B200 (tools/microbench.cu): REDUX ~21 cycles and
+// NOT pipelined (five REDUX.OR broadcasts cost 127), ballot + ffs ~65, shfl ~30 -- the classic REDUX, REDUX,
+// ballot, ffs, 3 x shfl chain is ~180.  When several lanes hold the maximum (rare: distinct points almost never share a
+// min-distance) they race on the slot and a second REDUX over the tie keys picks the one that rewrites it.  Tie keys are
+// unique among real candidates; lanes without one pass (0, 0).  `slot` must not be reused by the next call (toggle).
+__device__ __forceinline__ unsigned fc_argmax(uint4 *slot, unsigned v, unsigned t, unsigned p0, unsigned p1, unsigned p2,
+                                              uint4 &w) {
+    const unsigned vmax = __reduce_max_sync(0xffffffffu, v);
+    const bool eq = v == vmax;
+    if (eq) *slot = make_uint4(t, p0, p1, p2);
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    __syncwarp();
+    if (bal & (bal - 1u)) {  // warp-uniform
+        const unsigned tmax = __reduce_max_sync(0xffffffffu, eq ? t : 0u);
+        if (eq && t == tmax) *slot = make_uint4(t, p0, p1, p2);
+        __syncwarp();
+    }
+    w = *slot;
+    return vmax;
+}
+
+// This warp's candidate of pick k = arg-max over its lanes' candidates (value bits, tie key = ~index or 0 for "none",
+// coordinates): the winning lane writes the 32-byte record, 16 lanes push it into the record table of every CTA of
+// the cluster (ra / rb: this lane's remote record / mbarrier address for the parity of k).
+__device__ __forceinline__ void fc_publish(FcShared &sh, int k, int warp, int lane, unsigned ra, unsigned rb, unsigned v,
+                                           unsigned t, float x, float y, float z) {
+    uint4 *st = sh.stage[k & 1][warp];
+    const unsigned vmax = __reduce_max_sync(0xffffffffu, v);
+    const bool eq = v == vmax;
+    if (eq) {
+        st[0] = make_uint4(t ? vmax : 0u, t, __float_as_uint(x), __float_as_uint(y));
+        st[1] = make_uint4(__float_as_uint(z), 0u, 0u, 0u);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    __syncwarp();
+    if (bal & (bal - 1u)) {  // warp-uniform
+        const unsigned tmax = __reduce_max_sync(0xffffffffu, eq ? t : 0u);
+        if (eq && t == tmax) {
+            st[0] = make_uint4(t ? vmax : 0u, t, __float_as_uint(x), __float_as_uint(y));
+            st[1] = make_uint4(__float_as_uint(z), 0u, 0u, 0u);
+        }
+        __syncwarp();
+    }
+    if (lane < 2 * FC_CS) fc_st_async16(ra, st[lane & 1], rb);
+}
+// wait for the 32 records of pick k and reduce them: the same winner in every warp of the cluster
+__device__ __forceinline__ void fc_collect(FcShared &sh, int k, int warp, int lane, bool armer, unsigned &sel, float &sx,
+                                           float &sy, float &sz) {
+    const int par = k & 1;
+    const unsigned parity = (unsigned)(((k - 1) >> 1) & 1);
+    const unsigned bar = fc_s32(&sh.bar[par]);
+    fc_mbar_wait(bar, parity);
+    const uint4 a = sh.rec[par][lane][0];
+    const unsigned zb = sh.rec[par][lane][1].x;
+    if (armer) fc_mbar_arm(bar, FC_TX);  // pick k + 2 (nobody can publish it before this CTA has published k + 1)
+    uint4 w;
+    fc_argmax(&sh.win[par][warp], a.x, a.y, a.z, a.w, zb, w);
+    sel = 0xffffffffu - w.x;
+    sx = __uint_as_float(w.y);
+    sy = __uint_as_float(w.z);
+    sz = __uint_as_float(w.w);
+}
+// this lane's remote addresses (lanes < 16: destination CTA lane / 2, record half lane & 1) for both parities
+__device__ __forceinline__ void fc_remote(FcShared &sh, int gw, int lane, unsigned (&ra)[2], unsigned (&rb)[2]) {
+    const unsigned dest = ((unsigned)lane >> 1) & (FC_CS - 1), half = (unsigned)lane & 1u;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        ra[p] = fc_mapa(fc_s32(&sh.rec[p][gw][half]), dest);
+        rb[p] = fc_mapa(fc_s32(&sh.bar[p]), dest);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bucket-pruned FPS over the cell-sorted cloud (see fps_grid_kernel in grid.cu for the pruning argument):
+// bucket id = lane * 32 + (warp of the cluster), one bucket of 32 * PPL points per thread.
+// RES: the warp's 32 buckets (points + min-distances) live in this CTA's shared memory.
+// ---------------------------------------------------------------------------------------------------------
+template <int PPL, bool RES>
+__global__ void __launch_bounds__(FC_T, 1)
+fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
+                        const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
+                        int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
+                        uint8_t *__restrict__ new_pad, int *__restrict__ new_len32) {
+    constexpr int BS = 32 * PPL, D = PPL <= 2 ? 2 : 1;
+    extern __shared__ __align__(16) unsigned char fc_smem[];
+    FcShared &sh = *reinterpret_cast<FcShared *>(fc_smem);
+    float4 *spts = reinterpret_cast<float4 *>(fc_smem + sizeof(FcShared));  // [FC_WPC * 32 * BS]
+    float *smin = reinterpret_cast<float *>(spts + (RES ? FC_WPC * 32 * BS : 0));
+
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = fc_rank();
+    const int gw = (int)rank * FC_WPC + warp;
+    const int len = desc[b].nvalid;
+    const int kn = min(len, K);
+    const int nb = (len + BS - 1) / BS;  // <= 1024
+    const float4 *P = sorted + (size_t)b * npad;
+    float *M = mind + (size_t)b * npad;
+    const size_t ob = (size_t)b * K;
+    const float INF = __int_as_float(0x7f800000);
+    const bool writer = rank == 0 && tid == 0;
+    fc_setup(sh, tid);
+    unsigned ra[2], rb[2];
+    fc_remote(sh, gw, lane, ra, rb);
+    int tog = 0;
+
+    // ---- prologue: tiles -> shared memory, bucket boxes, min-distances = +inf (sentinels 0) ----
+    float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+    unsigned maxbits = 0u, argidx = 0xffffffffu;
+    const bool owns = lane * FC_NW + gw < nb;
+    for (int L = 0; L < 32; ++L) {
+        const int bk = L * FC_NW + gw;
+        if (bk >= nb) break;  // warp-uniform
+        float l0 = INF, l1 = INF, l2 = INF, h0 = -INF, h1 = -INF, h2 = -INF;
+        unsigned mi = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) {
+            const int i = bk * BS + j * 32 + lane;
+            const float4 p = P[i];
+            const unsigned id = __float_as_uint(p.w);
+            const bool valid = id != 0x7fffffffu;
+            if (RES) {
+                spts[(warp * 32 + L) * BS + j * 32 + lane] = p;
+                smin[(warp * 32 + L) * BS + j * 32 + lane] = valid ? INF : 0.f;
+            } else {
+                M[i] = valid ? INF : 0.f;
+            }
+            if (valid) {
+                l0 = fminf(l0, p.x); h0 = fmaxf(h0, p.x);
+                l1 = fminf(l1, p.y); h1 = fmaxf(h1, p.y);
+                l2 = fminf(l2, p.z); h2 = fmaxf(h2, p.z);
+                mi = min(mi, id);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, o)); h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, o));
+            l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o));
+            l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
+        }
+        mi = __reduce_min_sync(0xffffffffu, mi);
+        if (lane == L) {
+            lox = l0; loy = l1; loz = l2; hix = h0; hiy = h1; hiz = h2;
+            maxbits = 0x7f800000u;  // +inf: every bucket is touched by the first sample
+            argidx = mi;
+        }
+    }
+
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (len > 0) {
+        const float4 p0 = xyz4[(size_t)b * N];
+        sx = p0.x; sy = p0.y; sz = p0.z;
+    }
+    if (writer && kn > 0) {
+        if (idx64) idx64[ob] = 0;
+        if (idx32) idx32[ob] = 0;
+        if (new_xyz4) new_xyz4[ob] = make_float4(sx, sy, sz, 0.f);
+        if (new_pad) new_pad[ob] = 0;
+    }
+    fc_cluster_sync();  // every CTA's mbarriers are initialised and armed before the first record arrives
+
+#ifdef DPM_FC_PROFILE
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#endif
+    for (int k = 1; k < kn; ++k) {
+        // ---- phase A, the critical path: box tests, update of the touched tiles, this warp's candidate ----
+        FC_TICK(7);
+        bool act = false;
+        if (owns) {  // can my bucket change?  (d2 >= lb for every point of the box)
+            const float dx = fmaxf(fmaxf(lox - sx, sx - hix), 0.f);
+            const float dy = fmaxf(fmaxf(loy - sy, sy - hiy), 0.f);
+            const float dz = fmaxf(fmaxf(loz - sz, sz - hiz), 0.f);
+            const float lb = (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound of every d2
+            act = lb < __uint_as_float(maxbits);
+        }
+        const unsigned mask0 = __ballot_sync(0xffffffffu, act);
+        // lane-level candidate (value bits, tie key = ~index): the cached maximum of my bucket while it is untouched,
+        // merged with my points of every touched tile of the warp
+        const bool cached = owns && !act && argidx != 0xffffffffu;
+        unsigned cb = cached ? maxbits : 0u, cn = cached ? 0xffffffffu - argidx : 0u;
+        float cx = ax, cy = ay, cz = az;
+        unsigned mask = mask0;
+        FC_TICK(0);
+        while (mask) {
+            int Ls[D];
+            float4 p[D][PPL];
+            float m[D][PPL];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                Ls[d] = -1;
+                if (mask) {
+                    Ls[d] = 31 - __clz(mask);
+                    mask &= ~(1u << Ls[d]);
+#pragma unroll
+                    for (int j = 0; j < PPL; ++j) {
+                        if (RES) {
+                            const int o = (warp * 32 + Ls[d]) * BS + j * 32 + lane;
+                            p[d][j] = spts[o];
+                            m[d][j] = smin[o];
+                        } else {
+                            const int o = (Ls[d] * FC_NW + gw) * BS + j * 32 + lane;
+                            p[d][j] = P[o];
+                            m[d][j] = M[o];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if (Ls[d] < 0) continue;  // warp-uniform
+                unsigned bb = 0u, bn = 0u;
+                float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+                for (int j = 0; j < PPL; ++j) {
+                    const float dd = d2_exact(sx, sy, sz, p[d][j].x, p[d][j].y, p[d][j].z);
+                    const float nm = fminf(m[d][j], dd);
+                    if (nm < m[d][j]) {
+                        if (RES) smin[(warp * 32 + Ls[d]) * BS + j * 32 + lane] = nm;
+                        else M[(Ls[d] * FC_NW + gw) * BS + j * 32 + lane] = nm;
+                    }
+                    const unsigned bits = __float_as_uint(nm);  // nm >= 0: the bit pattern is order preserving
+                    const unsigned nid = 0xffffffffu - __float_as_uint(p[d][j].w);
+                    if (bits > bb || (bits == bb && nid > bn)) { bb = bits; bn = nid; bx = p[d][j].x; by = p[d][j].y; bz = p[d][j].z; }
+                }
+                if (bb > cb || (bb == cb && bn > cn)) { cb = bb; cn = bn; cx = bx; cy = by; cz = bz; }
+                if (!RES) {  // tiles in L2: the bucket's new maximum now, while its points are in registers
+                    uint4 w;
+                    const unsigned tb = fc_argmax(&sh.tmp[tog][warp], bb, bn, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz), w);
+                    tog ^= 1;
+                    if (lane == Ls[d]) {
+                        maxbits = tb; argidx = 0xffffffffu - w.x;
+                        ax = __uint_as_float(w.y); ay = __uint_as_float(w.z); az = __uint_as_float(w.w);
+                    }
+                }
+            }
+        }
+        FC_TICK(1);
+        fc_publish(sh, k, warp, lane, (k & 1) ? ra[1] : ra[0], (k & 1) ? rb[1] : rb[0], cb, cn, cx, cy, cz);
+        FC_TICK(3);
+        // ---- phase B, in the shadow of the exchange: the touched buckets' new maxima, for their owners ----
+        if (RES) {
+            mask = mask0;
+            while (mask) {
+                const int L = 31 - __clz(mask);
+                mask &= ~(1u << L);
+                unsigned bb = 0u, bn = 0u;
+                float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+                for (int j = 0; j < PPL; ++j) {
+                    const int o = (warp * 32 + L) * BS + j * 32 + lane;
+                    const float4 q = spts[o];
+                    const unsigned bits = __float_as_uint(smin[o]);
+                    const unsigned nid = 0xffffffffu - __float_as_uint(q.w);
+                    if (bits > bb || (bits == bb && nid > bn)) { bb = bits; bn = nid; bx = q.x; by = q.y; bz = q.z; }
+                }
+                uint4 w;
+                const unsigned tb = fc_argmax(&sh.tmp[tog][warp], bb, bn, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz), w);
+                tog ^= 1;
+                if (lane == L) {
+                    maxbits = tb; argidx = 0xffffffffu - w.x;
+                    ax = __uint_as_float(w.y); ay = __uint_as_float(w.z); az = __uint_as_float(w.w);
+                }
+            }
+        }
+        // ---- the cluster-wide winner ----
+        FC_TICK(4);
+        unsigned sel;
+        fc_collect(sh, k, warp, lane, tid == 0, sel, sx, sy, sz);
+        FC_TICK(5);
+        if (gw == 0) {  // one store per lane
+            if (lane == 0 && idx64) idx64[ob + k] = (int64_t)sel;
+            if (lane == 1 && idx32) idx32[ob + k] = (int32_t)sel;
+            if (lane == 2 && new_xyz4) new_xyz4[ob + k] = make_float4(sx, sy, sz, 0.f);
+            if (lane == 3 && new_pad) new_pad[ob + k] = 0;
+        }
+    }
+#ifdef DPM_FC_PROFILE
+    if (lane == 0 && b == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&fc_prof[i], (unsigned long long)pacc[i]);
+    if (writer && b == 0) atomicAdd(&fc_prof[8], (unsigned long long)(kn - 1));
+#endif
+    if (rank == 0) {
+        for (int k = kn + tid; k < K; k += FC_T) {  // K > len: idx -1, zero rows, padded
+            if (idx64) idx64[ob + k] = -1;
+            if (idx32) idx32[ob + k] = -1;
+            if (new_xyz4) new_xyz4[ob + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (new_pad) new_pad[ob + k] = 1;
+        }
+        if (tid == 0 && new_len32) new_len32[b] = kn;
+    }
+    fc_cluster_sync();  // no CTA may exit while a peer can still store into its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small clouds: P points per thread in registers, point i = j * 1024 + (warp of the cluster) * 32 + lane
+// ---------------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(FC_T, 1)
+fps_brute_cluster_kernel(const float4 *__restrict__ xyz4, int N, const int *__restrict__ len32, int K,
+                         int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
+                         uint8_t *__restrict__ new_pad, int *__restrict__ new_len32) {
+    __shared__ FcShared sh;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = fc_rank();
+    const int gw = (int)rank * FC_WPC + warp;
+    const int len = len32 ? min(len32[b], N) : N;
+    const int kn = min(len, K);
+    const float4 *pts = xyz4 + (size_t)b * N;
+    const size_t ob = (size_t)b * K;
+    const bool writer = rank == 0 && tid == 0;
+    fc_setup(sh, tid);
+    unsigned ra[2], rb[2];
+    fc_remote(sh, gw, lane, ra, rb);
+
+    float x[P], y[P], z[P], m[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int i = j * (FC_NW * 32) + gw * 32 + lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        m[j] = 0.f;  // points past `len` never win: min-distance 0 and a higher index than any valid point
+        if (i < len) {
+            p = pts[i];
+            m[j] = __int_as_float(0x7f800000);
+        }
+        x[j] = p.x; y[j] = p.y; z[j] = p.z;
+    }
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (len > 0) {
+        const float4 p0 = pts[0];
+        sx = p0.x; sy = p0.y; sz = p0.z;
+    }
+    if (writer && kn > 0) {
+        if (idx64) idx64[ob] = 0;
+        if (idx32) idx32[ob] = 0;
+        if (new_xyz4) new_xyz4[ob] = make_float4(sx, sy, sz, 0.f);
+        if (new_pad) new_pad[ob] = 0;
+    }
+    fc_cluster_sync();
+
+    for (int k = 1; k < kn; ++k) {
+        float bm = 0.f;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            m[j] = fminf(m[j], d2_exact(sx, sy, sz, x[j], y[j], z[j]));
+            bm = fmaxf(bm, m[j]);
+        }
+        int jj = 0;
+#pragma unroll
+        for (int j = P - 1; j >= 0; --j)
+            if (m[j] == bm) jj = j;  // lowest j = lowest index among this thread's ties
+        float px = x[0], py = y[0], pz = z[0];
+#pragma unroll
+        for (int j = 1; j < P; ++j)
+            if (jj == j) { px = x[j]; py = y[j]; pz = z[j]; }
+        // bm >= 0: the bit pattern is order preserving; tie key = ~index (never 0: index < 2^31)
+        const unsigned nid = 0xffffffffu - (unsigned)(jj * (FC_NW * 32) + gw * 32 + lane);
+        fc_publish(sh, k, warp, lane, (k & 1) ? ra[1] : ra[0], (k & 1) ? rb[1] : rb[0], __float_as_uint(bm), nid, px, py, pz);
+        unsigned sel;
+        fc_collect(sh, k, warp, lane, tid == 0, sel, sx, sy, sz);
+        if (gw == 0) {  // one store per lane
+            if (lane == 0 && idx64) idx64[ob + k] = (int64_t)sel;
+            if (lane == 1 && idx32) idx32[ob + k] = (int32_t)sel;
+            if (lane == 2 && new_xyz4) new_xyz4[ob + k] = make_float4(sx, sy, sz, 0.f);
+            if (lane == 3 && new_pad) new_pad[ob + k] = 0;
+        }
+    }
+    if (rank == 0) {
+        for (int k = kn + tid; k < K; k += FC_T) {
+            if (idx64) idx64[ob + k] = -1;
+            if (idx32) idx32[ob + k] = -1;
+            if (new_xyz4) new_xyz4[ob + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (new_pad) new_pad[ob + k] = 1;
+        }
+        if (tid == 0 && new_len32) new_len32[b] = kn;
+    }
+    fc_cluster_sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// policy + launchers
+// ---------------------------------------------------------------------------------------------------------
+static std::atomic<int> g_fps_mode{0};  // 0 auto, 1 one CTA per cloud, 2 cluster per cloud
+
+static size_t fc_grid_smem(int ppl, bool res) {
+    return sizeof(FcShared) + (res ? (size_t)FC_WPC * 32 * 32 * ppl * (sizeof(float4) + sizeof(float)) : 0);
+}
+
+// clouds whose clusters are co-resident: what the hardware can place of the largest cluster kernel (8 CTAs x 166 KB
+// of shared memory, one GPC per cluster), asked once per device
+int fps_cluster_capacity() {
+    static thread_local int cached[64];
+    const int dev = current_device() & 63;
+    if (cached[dev] == 0) {
+        int n = 0;
+        auto kern = fps_grid_cluster_kernel<2, true>;
+        const size_t smem = fc_grid_smem(2, true);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(FC_CS, 64, 1);
+        cfg.blockDim = dim3(FC_T, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = FC_CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = device_sm_count() / (2 * FC_CS);  // conservative
+        }
+        cached[dev] = n < 1 ? 1 : n;
+    }
+    return cached[dev];
+}
+
+bool fps_cluster_mode(int B) {
+    static const char *env = getenv("DPM_FPS_MODE");  // developer A/B switch: 1 / 2 as dpm_set_fps_mode
+    int mode = g_fps_mode.load(std::memory_order_relaxed);
+    if (mode == 0 && env) mode = atoi(env);
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    // few clouds: 8 SMs each, all clusters resident at once.  Larger batches are throughput work: one SM per cloud
+    // and the rest of the chip for the other kernels / streams (a second wave of clusters would double the latency).
+    return B <= fps_cluster_capacity();
+}
+
+template <typename Kern, typename... Args>
+static int fc_launch(Kern kern, size_t smem, int B, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(FC_CS, B, 1);
+    cfg.blockDim = dim3(FC_T, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = FC_CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DPM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    count_launch("fps", st);
+    return DPM_OK;
+}
+
+template <int PPL, bool RES>
+static int fps_grid_cluster_t(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
+                              float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
+    auto kern = fps_grid_cluster_kernel<PPL, RES>;
+    const size_t smem = fc_grid_smem(PPL, RES);
+    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
+    const unsigned long long devbit = 1ull << (current_device() & 63);
+    if (!(configured & devbit)) {
+        DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured |= devbit;
+    }
+    return fc_launch(kern, smem, B, st, (const float4 *)g.sorted, g.mind, g.npad, (const GridDesc *)g.desc, xyz4, N, K, idx64,
+                     idx32, new_xyz4, new_pad, new_len32);
+}
+
+int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
+                            float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
+    if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
+    prof_note(N, K);
+    switch (grid_ppl(N)) {
+        case 1: return fps_grid_cluster_t<1, true>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 2: return fps_grid_cluster_t<2, true>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 4: return fps_grid_cluster_t<4, false>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 8: return fps_grid_cluster_t<8, false>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+    }
+    return fail(DPM_ERR_UNSUPPORTED, "fps: no cluster kernel for N=%d", N);
+}
+
+int fps_brute_cluster_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64, int32_t *idx32,
+                             float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
+    prof_note(N, K);
+#define DPM_FB_CASE(p)                                                                                              \
+    if (N <= p * FC_NW * 32)                                                                                        \
+        return fc_launch(fps_brute_cluster_kernel<p>, 0, B, st, xyz4, N, len32, K, idx64, idx32, new_xyz4, new_pad, \
+                         new_len32);
+    DPM_FB_CASE(1) DPM_FB_CASE(2) DPM_FB_CASE(4) DPM_FB_CASE(8)
+#undef DPM_FB_CASE
+    return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the register-resident cluster limit %d", N, FPS_BRUTE_CLUSTER_MAX_N);
+}
+
+}  // namespace dpm
+
+#ifdef DPM_FC_PROFILE
+extern "C" int dpm_debug_fc_profile(unsigned long long *out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, dpm::fc_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(dpm::fc_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+extern "C" int dpm_fps_cluster_capacity(void) { return dpm::fps_cluster_capacity(); }
+extern "C" void dpm_set_fps_mode(int mode) { dpm::g_fps_mode.store(mode < 0 || mode > 2 ? 0 : mode, std::memory_order_relaxed); }

@@ -428,6 +428,8 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
                     float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
     if (B <= 0 || N <= 0 || K <= 0) return fail(DPM_ERR_SHAPE, "fps: bad shape B=%d N=%d K=%d", B, N, K);
     if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
+    if (fps_cluster_mode(B))  // few clouds: 8 SMs per cloud instead of one (fps_cluster.cu)
+        return fps_grid_cluster_launch(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
     const int ppl = grid_ppl(N);
     prof_note(N, K);
 #define DPM_FG_ARGS g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, new_pad, new_len32

@@ -34,6 +34,12 @@ def _ws(device, nbytes):
     return _C.workspaces.get(device, nbytes, f"ops{_C.stream_ptr()}")
 
 
+def set_fps_mode(mode: int = 0) -> None:
+    """How every FPS of the library maps a cloud onto the chip (`dpm_set_fps_mode`): 0 auto (a cluster of 8 SMs per
+    cloud while the batch is <= 16 clouds, else one SM per cloud), 1 always one SM, 2 always a cluster.  Same picks."""
+    _C.lib().dpm_set_fps_mode(int(mode))
+
+
 def sample_farthest_points(points: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                            K: Union[int, list, torch.Tensor] = 50, random_start_point: bool = False):
     """pytorch3d.ops.sample_farthest_points: (N,P,D) -> (sampled (N,K,D), idx (N,K) int64, -1 padded)."""

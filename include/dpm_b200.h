@@ -68,6 +68,14 @@ int dpm_prof_end(char *buf, size_t buf_bytes);
 int dpm_fps_f32(const float *points, int B, int N, int D, const int64_t *lengths, int K,
                 int64_t *idx_out, float *sampled_out, void *ws, size_t ws_bytes, dpm_stream_t stream);
 size_t dpm_fps_workspace_bytes(int B, int N, int D, int K);
+/* How a cloud is mapped onto the chip by every FPS in this library (same picks either way): 0 = auto (a
+ * cluster of 8 SMs per cloud while all clouds of the call fit the chip at once, B <= dpm_fps_cluster_capacity() -- the latency
+ * shape of pipeline/infer.py's batch of 1; one SM per cloud for larger batches, which leaves the other SMs
+ * to the kernels of concurrent streams), 1 = always one SM per cloud, 2 = always a cluster.  Process-wide. */
+void dpm_set_fps_mode(int mode);
+/* clouds per call up to which mode 0 takes the cluster mapping: the number of 8-CTA clusters of the largest FPS
+ * kernel the current device can hold at once (cudaOccupancyMaxActiveClusters) */
+int dpm_fps_cluster_capacity(void);
 
 /* [t3d] knn_points(p1 (B,S,D1), p2 (B,N,D2), lengths1, lengths2, K) -> dists (B,S,K)
  * squared, ascending by (d2, index); idx (B,S,K) int64.  Only xyz (first 3 columns) is

@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=[1, 2], ids=["one-sm", "cluster"])
+def fps_mode(request):
+    """every FPS test runs on both mappings: one CTA per cloud (grid.cu / fps.cu) and an 8-CTA cluster per cloud
+    (fps_cluster.cu)"""
+    ops.set_fps_mode(request.param)
+    yield request.param
+    ops.set_fps_mode(0)
+
+
 def _cloud(kind, seed, n):
     c = data.kitti_shape_cloud(seed, n) if kind == "kitti" else data.uniform_cube_cloud(seed, n)
     return c.T.contiguous()  # (n, 3)
@@ -19,14 +28,14 @@ def _cloud(kind, seed, n):
 
 @pytest.mark.parametrize("n,k", [(16, 16), (64, 16), (256, 64), (1000, 100), (1024, 256), (4096, 1024),
                                  (14500, 4096), (20000, 512), (65536, 4096), (100000, 1024), (131072, 64)])
-def test_fps_bit_exact(n, k):
+def test_fps_bit_exact(n, k, fps_mode):
     pts = torch.stack([_cloud("kitti", n, n), _cloud("cube", n + 1, n)])
     want = IO.fps(pts, None, k)
     _, got = ops.sample_farthest_points(pts.to(DEV), K=k)
     assert torch.equal(got.cpu(), want)
 
 
-def test_fps_lengths_padding_and_gather():
+def test_fps_lengths_padding_and_gather(fps_mode):
     n, k = 3000, 700
     pts = torch.stack([_cloud("kitti", 1, n), _cloud("cube", 2, n), _cloud("kitti", 3, n)])
     pts = torch.cat([pts, torch.arange(n, dtype=torch.float32).view(1, n, 1).expand(3, n, 1)], dim=2)  # D = 4
@@ -40,7 +49,7 @@ def test_fps_lengths_padding_and_gather():
     assert torch.equal(out.cpu(), ref)  # masked_gather: -1 rows are zero
 
 
-def test_fps_duplicates_first_maximum():
+def test_fps_duplicates_first_maximum(fps_mode):
     pts = torch.zeros(1, 600, 3)
     pts[0, 300:] = 1.0
     want = IO.fps(pts, None, 5)
@@ -48,7 +57,7 @@ def test_fps_duplicates_first_maximum():
     assert got.cpu().tolist() == want.tolist() == [[0, 300, 0, 0, 0]]
 
 
-def test_fps_batch_of_full_frames():
+def test_fps_batch_of_full_frames(fps_mode):
     pts = torch.stack([_cloud("kitti", s, 65536) for s in range(3)])
     want = IO.fps(pts, None, 4096)
     _, got = ops.sample_farthest_points(pts.to(DEV), K=4096)
@@ -168,14 +177,14 @@ def _lattice(n, seed):
 
 
 @pytest.mark.parametrize("n,k", [(2048, 300), (5000, 1000), (40000, 600)])
-def test_fps_grid_ties_on_lattice(n, k):
+def test_fps_grid_ties_on_lattice(n, k, fps_mode):
     pts = torch.stack([_lattice(n, 1), _lattice(n, 2)])
     want = IO.fps(pts, None, k)
     _, got = ops.sample_farthest_points(pts.to(DEV), K=k)
     assert torch.equal(got.cpu(), want)
 
 
-def test_fps_grid_lengths_and_degenerate_clouds():
+def test_fps_grid_lengths_and_degenerate_clouds(fps_mode):
     n, k = 6000, 900
     pts = torch.stack([_cloud("kitti", 1, n), _cloud("cube", 2, n), torch.zeros(n, 3), _cloud("kitti", 3, n),
                        _cloud("cube", 4, n) * torch.tensor([1.0, 0.0, 0.0])])  # identical points; a line
@@ -208,7 +217,7 @@ def test_hybrid_grid_queries_outside_the_cloud_and_huge_radius():
         assert torch.equal(got.cpu(), want), r
 
 
-def test_grid_results_are_deterministic():
+def test_grid_results_are_deterministic(fps_mode):
     """the cell-sorted layout depends on atomic order; the results must not"""
     pts = torch.stack([_cloud("kitti", 5, 65536), _lattice(65536, 6)]).to(DEV)
     ref_f = ops.sample_farthest_points(pts, K=1024)[1]
