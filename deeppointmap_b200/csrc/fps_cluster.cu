@@ -40,9 +40,10 @@ static_assert(FC_NW == 32, "the record reduce takes one record per lane");
 constexpr unsigned FC_TX = FC_NW * 32u;   // bytes that complete one pick's mbarrier phase
 
 struct __align__(16) FcShared {
-    uint4 rec[2][FC_NW][2];     // [parity][warp of the cluster][half]: {value bits, ~index, x, y}, {z, -, -, -}
+    uint4 rec[2][FC_NW][2];     // [parity][warp of the cluster]: {value bits, ~index, x, y}, {z, second value of the warp, -, -}
     uint4 stage[2][FC_WPC][2];  // [parity][warp]: this warp's record, written by its winning lane, pushed out by 16 lanes
-    uint4 win[2][FC_WPC];       // [parity][warp]: the cluster-wide winner {~index, x, y, z} as this warp reduced it
+    uint4 win[2][FC_WPC][3];    // [parity][warp]: the round's result as this warp reduced it: winner {~index, x, y, z},
+                                //   {second value of the winner's warp}, runner-up {~index, x, y, z}
     uint4 tmp[2][FC_WPC];       // [toggle][warp]: broadcast slot of the bucket-level arg-max
     unsigned long long bar[2];
 };
@@ -110,69 +111,130 @@ __device__ __forceinline__ void fc_setup(FcShared &sh, int tid) {
     }
 }
 
-// Warp arg-max of (value bits, tie key) -- both "larger wins" -- with a three-word payload.  One REDUX finds the
-// largest value; the lane that holds it drops {tie key, payload} into a shared-memory slot that every lane reads
-// back (STS + LDS broadcast, ~40 cycles).  Measured alternatives on B200 (tools/microbench.cu): REDUX ~21 cycles and
-// NOT pipelined (five REDUX.OR broadcasts cost 127), ballot + ffs ~65, shfl ~30 -- the classic REDUX, REDUX,
-// ballot, ffs, 3 x shfl chain is ~180.  When several lanes hold the maximum (rare: distinct points almost never share a
-// min-distance) they race on the slot and a second REDUX over the tie keys picks the one that rewrites it.  Tie keys are
-// unique among real candidates; lanes without one pass (0, 0).  `slot` must not be reused by the next call (toggle).
-__device__ __forceinline__ unsigned fc_argmax(uint4 *slot, unsigned v, unsigned t, unsigned p0, unsigned p1, unsigned p2,
-                                              uint4 &w) {
-    const unsigned vmax = __reduce_max_sync(0xffffffffu, v);
-    const bool eq = v == vmax;
-    if (eq) *slot = make_uint4(t, p0, p1, p2);
-    const unsigned bal = __ballot_sync(0xffffffffu, eq);
-    __syncwarp();
-    if (bal & (bal - 1u)) {  // warp-uniform
-        const unsigned tmax = __reduce_max_sync(0xffffffffu, eq ? t : 0u);
-        if (eq && t == tmax) *slot = make_uint4(t, p0, p1, p2);
-        __syncwarp();
+// ---- the arg-max machinery -------------------------------------------------------------------------------
+// Candidates are ordered by (value bits, tie key), both "larger wins": value = fp32 min-distance (>= 0, so its bit
+// pattern is order preserving), tie key = ~original index (first maximum = lowest index; 0 = "no candidate").
+// A warp arg-max is ONE REDUX over the values; the lane that holds the maximum drops its payload into a
+// shared-memory slot that the others read back (STS + LDS, ~40 cycles).  Measured alternatives on B200
+// (tools/microbench.cu): REDUX ~21 cycles and not pipelined (five REDUX.OR broadcasts: 127), ballot + ffs ~65,
+// shfl ~30 -- the classic REDUX, REDUX, ballot, ffs, 3 x shfl chain is ~180.  When several lanes hold the maximum
+// (rare: distinct points almost never share a min-distance) they race on the slot and a second REDUX over the tie
+// keys picks the one that rewrites it.
+//
+// TWO PICKS PER ROUND.  The exchange across the cluster (~400 cycles of st.async flight + mbarrier wake-up) is the
+// largest item of a pick, so a round tries to settle two: next to its best candidate every lane / bucket / warp
+// tracks the VALUE of its second best point, and a warp's record carries the second best value of the warp.  After
+// the exchange every warp knows the winner G1, the best G2 of the other 31 warps, and the second value v2 of G1's
+// warp.  If value(G2) > v2, G2 is the strict global runner-up; if moreover d2(G1, G2) >= value(G2), inserting G1
+// does not lower G2's min-distance -- and since min-distances only ever shrink, G2 is exactly the next farthest
+// point (same value, same tie-break) and is emitted in the same round.  Otherwise the round yields one pick, as
+// before.  Every warp evaluates the same test on the same 32 records, so the cluster stays in step.  On KITTI-shaped
+// clouds ~9 of 10 rounds yield two picks.
+struct FcCand {
+    unsigned b, n, b2;  // best: value bits, tie key; second best: value bits
+    float x, y, z;      // coordinates of the best
+};
+__device__ __forceinline__ void fc_merge(FcCand &c, unsigned bits, unsigned nid, float x, float y, float z) {
+    if (bits > c.b || (bits == c.b && nid > c.n)) {
+        c.b2 = c.b; c.b = bits; c.n = nid; c.x = x; c.y = y; c.z = z;
+    } else {
+        c.b2 = max(c.b2, bits);
     }
-    w = *slot;
-    return vmax;
 }
 
-// This warp's candidate of pick k = arg-max over its lanes' candidates (value bits, tie key = ~index or 0 for "none",
-// coordinates): the winning lane writes the 32-byte record, 16 lanes push it into the record table of every CTA of
-// the cluster (ra / rb: this lane's remote record / mbarrier address for the parity of k).
-__device__ __forceinline__ void fc_publish(FcShared &sh, int k, int warp, int lane, unsigned ra, unsigned rb, unsigned v,
-                                           unsigned t, float x, float y, float z) {
-    uint4 *st = sh.stage[k & 1][warp];
-    const unsigned vmax = __reduce_max_sync(0xffffffffu, v);
-    const bool eq = v == vmax;
-    if (eq) {
-        st[0] = make_uint4(t ? vmax : 0u, t, __float_as_uint(x), __float_as_uint(y));
-        st[1] = make_uint4(__float_as_uint(z), 0u, 0u, 0u);
-    }
+// (max, second value, arg) of one bucket from the lanes' candidates over its points; only `owner` keeps the result.
+// `slot` must not be the slot of the previous call (toggle).
+__device__ __forceinline__ void fc_bucket(uint4 *slot, const FcCand &c, bool owner, unsigned &maxbits, unsigned &max2bits,
+                                          unsigned &argidx, float &ax, float &ay, float &az) {
+    const unsigned vmax = __reduce_max_sync(0xffffffffu, c.b);
+    const bool eq = c.b == vmax;
+    if (eq) *slot = make_uint4(c.n, __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z));
     const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    unsigned v2 = __reduce_max_sync(0xffffffffu, eq ? c.b2 : c.b);
     __syncwarp();
     if (bal & (bal - 1u)) {  // warp-uniform
-        const unsigned tmax = __reduce_max_sync(0xffffffffu, eq ? t : 0u);
-        if (eq && t == tmax) {
-            st[0] = make_uint4(t ? vmax : 0u, t, __float_as_uint(x), __float_as_uint(y));
-            st[1] = make_uint4(__float_as_uint(z), 0u, 0u, 0u);
+        v2 = vmax;
+        const unsigned tmax = __reduce_max_sync(0xffffffffu, eq ? c.n : 0u);
+        if (eq && c.n == tmax) *slot = make_uint4(c.n, __float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z));
+        __syncwarp();
+    }
+    if (owner) {
+        const uint4 w = *slot;
+        maxbits = vmax; max2bits = v2; argidx = 0xffffffffu - w.x;
+        ax = __uint_as_float(w.y); ay = __uint_as_float(w.z); az = __uint_as_float(w.w);
+    }
+}
+
+// This warp's record of round r: the winning lane writes it, 16 lanes push it into the record table of every CTA of
+// the cluster (ra / rb: this lane's remote record / mbarrier address for the parity of r).
+__device__ __forceinline__ void fc_publish(FcShared &sh, int r, int warp, int lane, unsigned ra, unsigned rb, const FcCand &c) {
+    uint4 *st = sh.stage[r & 1][warp];
+    const unsigned vmax = __reduce_max_sync(0xffffffffu, c.b);
+    const bool eq = c.b == vmax;
+    if (eq) {
+        st[0] = make_uint4(c.n ? vmax : 0u, c.n, __float_as_uint(c.x), __float_as_uint(c.y));
+        st[1] = make_uint4(__float_as_uint(c.z), 0u, 0u, 0u);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    unsigned v2 = __reduce_max_sync(0xffffffffu, eq ? c.b2 : c.b);  // second value of the warp when one lane holds the best
+    __syncwarp();
+    if (bal & (bal - 1u)) {  // warp-uniform
+        v2 = vmax;
+        const unsigned tmax = __reduce_max_sync(0xffffffffu, eq ? c.n : 0u);
+        if (eq && c.n == tmax) {
+            st[0] = make_uint4(c.n ? vmax : 0u, c.n, __float_as_uint(c.x), __float_as_uint(c.y));
+            st[1] = make_uint4(__float_as_uint(c.z), 0u, 0u, 0u);
         }
         __syncwarp();
     }
-    if (lane < 2 * FC_CS) fc_st_async16(ra, st[lane & 1], rb);
+    if (lane < 2 * FC_CS) {
+        uint4 q = st[lane & 1];
+        if (lane & 1) q.y = v2;
+        fc_st_async16(ra, q, rb);
+    }
 }
-// wait for the 32 records of pick k and reduce them: the same winner in every warp of the cluster
-__device__ __forceinline__ void fc_collect(FcShared &sh, int k, int warp, int lane, bool armer, unsigned &sel, float &sx,
-                                           float &sy, float &sz) {
-    const int par = k & 1;
-    const unsigned parity = (unsigned)(((k - 1) >> 1) & 1);
+
+struct FcPick {
+    unsigned sel1, sel2;
+    float x1, y1, z1, x2, y2, z2;
+    bool two;
+};
+// wait for the 32 records of round r and reduce them: the same result in every warp of the cluster
+__device__ __forceinline__ void fc_collect(FcShared &sh, int r, int warp, int lane, bool armer, bool allow_two, FcPick &o) {
+    const int par = r & 1;
+    const unsigned parity = (unsigned)(((r - 1) >> 1) & 1);
     const unsigned bar = fc_s32(&sh.bar[par]);
     fc_mbar_wait(bar, parity);
     const uint4 a = sh.rec[par][lane][0];
-    const unsigned zb = sh.rec[par][lane][1].x;
-    if (armer) fc_mbar_arm(bar, FC_TX);  // pick k + 2 (nobody can publish it before this CTA has published k + 1)
-    uint4 w;
-    fc_argmax(&sh.win[par][warp], a.x, a.y, a.z, a.w, zb, w);
-    sel = 0xffffffffu - w.x;
-    sx = __uint_as_float(w.y);
-    sy = __uint_as_float(w.z);
-    sz = __uint_as_float(w.w);
+    const uint2 zb = *reinterpret_cast<const uint2 *>(&sh.rec[par][lane][1]);
+    if (armer) fc_mbar_arm(bar, FC_TX);  // round r + 2 (nobody can publish it before this CTA has published r + 1)
+    uint4 *w = sh.win[par][warp];
+    const unsigned m1 = __reduce_max_sync(0xffffffffu, a.x);
+    const bool e1 = a.x == m1;
+    const unsigned m2 = __reduce_max_sync(0xffffffffu, e1 ? 0u : a.x);
+    const bool e2 = !e1 && a.x == m2;
+    if (e1) {
+        w[0] = make_uint4(a.y, a.z, a.w, zb.x);
+        w[1] = make_uint4(zb.y, 0u, 0u, 0u);
+    }
+    if (e2) w[2] = make_uint4(a.y, a.z, a.w, zb.x);
+    const unsigned bal1 = __ballot_sync(0xffffffffu, e1), bal2 = __ballot_sync(0xffffffffu, e2);
+    __syncwarp();
+    const bool multi = (bal1 & (bal1 - 1u)) != 0u;
+    if (multi) {  // warp-uniform: several warps offer the same value, the lowest index wins; one pick this round
+        const unsigned tmax = __reduce_max_sync(0xffffffffu, e1 ? a.y : 0u);
+        if (e1 && a.y == tmax) w[0] = make_uint4(a.y, a.z, a.w, zb.x);
+        __syncwarp();
+    }
+    const uint4 g1 = w[0], g2 = w[2];
+    const unsigned v2w = w[1].x;
+    o.sel1 = 0xffffffffu - g1.x;
+    o.x1 = __uint_as_float(g1.y); o.y1 = __uint_as_float(g1.z); o.z1 = __uint_as_float(g1.w);
+    bool two = allow_two && !multi && bal2 != 0u && (bal2 & (bal2 - 1u)) == 0u && m2 > 0u && m2 > v2w;
+    o.sel2 = 0xffffffffu - g2.x;
+    o.x2 = __uint_as_float(g2.y); o.y2 = __uint_as_float(g2.z); o.z2 = __uint_as_float(g2.w);
+    if (two) two = !(d2_exact(o.x1, o.y1, o.z1, o.x2, o.y2, o.z2) < __uint_as_float(m2));
+    o.two = two;
 }
 // this lane's remote addresses (lanes < 16: destination CTA lane / 2, record half lane & 1) for both parities
 __device__ __forceinline__ void fc_remote(FcShared &sh, int gw, int lane, unsigned (&ra)[2], unsigned (&rb)[2]) {
@@ -189,6 +251,14 @@ __device__ __forceinline__ void fc_remote(FcShared &sh, int gw, int lane, unsign
 // bucket id = lane * 32 + (warp of the cluster), one bucket of 32 * PPL points per thread.
 // RES: the warp's 32 buckets (points + min-distances) live in this CTA's shared memory.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fc_emit(size_t o, unsigned sel, float x, float y, float z, int lane, int64_t *idx64,
+                                        int32_t *idx32, float4 *new_xyz4, uint8_t *new_pad) {  // one store per lane
+    if (lane == 0 && idx64) idx64[o] = (int64_t)sel;
+    if (lane == 1 && idx32) idx32[o] = (int32_t)sel;
+    if (lane == 2 && new_xyz4) new_xyz4[o] = make_float4(x, y, z, 0.f);
+    if (lane == 3 && new_pad) new_pad[o] = 0;
+}
+
 template <int PPL, bool RES>
 __global__ void __launch_bounds__(FC_T, 1)
 fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
@@ -211,7 +281,6 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
     float *M = mind + (size_t)b * npad;
     const size_t ob = (size_t)b * K;
     const float INF = __int_as_float(0x7f800000);
-    const bool writer = rank == 0 && tid == 0;
     fc_setup(sh, tid);
     unsigned ra[2], rb[2];
     fc_remote(sh, gw, lane, ra, rb);
@@ -219,7 +288,7 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
 
     // ---- prologue: tiles -> shared memory, bucket boxes, min-distances = +inf (sentinels 0) ----
     float lox = 0.f, loy = 0.f, loz = 0.f, hix = 0.f, hiy = 0.f, hiz = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-    unsigned maxbits = 0u, argidx = 0xffffffffu;
+    unsigned maxbits = 0u, max2bits = 0u, argidx = 0xffffffffu;
     const bool owns = lane * FC_NW + gw < nb;
     for (int L = 0; L < 32; ++L) {
         const int bk = L * FC_NW + gw;
@@ -254,44 +323,50 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
         mi = __reduce_min_sync(0xffffffffu, mi);
         if (lane == L) {
             lox = l0; loy = l1; loz = l2; hix = h0; hiy = h1; hiz = h2;
-            maxbits = 0x7f800000u;  // +inf: every bucket is touched by the first sample
+            maxbits = max2bits = 0x7f800000u;  // +inf: every bucket is touched by the first sample
             argidx = mi;
         }
     }
 
-    float sx = 0.f, sy = 0.f, sz = 0.f;
+    // samples picked but not yet applied to the min-distances: s1, and s2 when the last round settled two picks
+    float s1x = 0.f, s1y = 0.f, s1z = 0.f, s2x = 0.f, s2y = 0.f, s2z = 0.f;
+    bool two = false;
     if (len > 0) {
         const float4 p0 = xyz4[(size_t)b * N];
-        sx = p0.x; sy = p0.y; sz = p0.z;
+        s1x = p0.x; s1y = p0.y; s1z = p0.z;
     }
-    if (writer && kn > 0) {
-        if (idx64) idx64[ob] = 0;
-        if (idx32) idx32[ob] = 0;
-        if (new_xyz4) new_xyz4[ob] = make_float4(sx, sy, sz, 0.f);
-        if (new_pad) new_pad[ob] = 0;
-    }
+    if (gw == 0 && kn > 0) fc_emit(ob, 0u, s1x, s1y, s1z, lane, idx64, idx32, new_xyz4, new_pad);
     fc_cluster_sync();  // every CTA's mbarriers are initialised and armed before the first record arrives
 
 #ifdef DPM_FC_PROFILE
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+    int rounds = 0;
 #endif
-    for (int k = 1; k < kn; ++k) {
+    int r = 1;
+    for (int k = 1; k < kn; ++r) {
         // ---- phase A, the critical path: box tests, update of the touched tiles, this warp's candidate ----
         FC_TICK(7);
         bool act = false;
         if (owns) {  // can my bucket change?  (d2 >= lb for every point of the box)
-            const float dx = fmaxf(fmaxf(lox - sx, sx - hix), 0.f);
-            const float dy = fmaxf(fmaxf(loy - sy, sy - hiy), 0.f);
-            const float dz = fmaxf(fmaxf(loz - sz, sz - hiz), 0.f);
-            const float lb = (dx * dx + dy * dy + dz * dz) * 0.99999f;  // conservative lower bound of every d2
-            act = lb < __uint_as_float(maxbits);
+            const float mb = __uint_as_float(maxbits);
+            float dx = fmaxf(fmaxf(lox - s1x, s1x - hix), 0.f);
+            float dy = fmaxf(fmaxf(loy - s1y, s1y - hiy), 0.f);
+            float dz = fmaxf(fmaxf(loz - s1z, s1z - hiz), 0.f);
+            act = (dx * dx + dy * dy + dz * dz) * 0.99999f < mb;  // conservative lower bound of every d2
+            if (two) {
+                dx = fmaxf(fmaxf(lox - s2x, s2x - hix), 0.f);
+                dy = fmaxf(fmaxf(loy - s2y, s2y - hiy), 0.f);
+                dz = fmaxf(fmaxf(loz - s2z, s2z - hiz), 0.f);
+                act = act || (dx * dx + dy * dy + dz * dz) * 0.99999f < mb;
+            }
         }
         const unsigned mask0 = __ballot_sync(0xffffffffu, act);
-        // lane-level candidate (value bits, tie key = ~index): the cached maximum of my bucket while it is untouched,
-        // merged with my points of every touched tile of the warp
+        // lane-level candidate: the cached (maximum, second value) of my bucket while it is untouched, merged with my
+        // points of every touched tile of the warp
+        FcCand c;
         const bool cached = owns && !act && argidx != 0xffffffffu;
-        unsigned cb = cached ? maxbits : 0u, cn = cached ? 0xffffffffu - argidx : 0u;
-        float cx = ax, cy = ay, cz = az;
+        c.b = cached ? maxbits : 0u; c.n = cached ? 0xffffffffu - argidx : 0u; c.b2 = cached ? max2bits : 0u;
+        c.x = ax; c.y = ay; c.z = az;
         unsigned mask = mask0;
         FC_TICK(0);
         while (mask) {
@@ -321,34 +396,29 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 if (Ls[d] < 0) continue;  // warp-uniform
-                unsigned bb = 0u, bn = 0u;
-                float bx = 0.f, by = 0.f, bz = 0.f;
+                FcCand t;
+                t.b = t.n = t.b2 = 0u; t.x = t.y = t.z = 0.f;
 #pragma unroll
                 for (int j = 0; j < PPL; ++j) {
-                    const float dd = d2_exact(sx, sy, sz, p[d][j].x, p[d][j].y, p[d][j].z);
-                    const float nm = fminf(m[d][j], dd);
+                    float nm = fminf(m[d][j], d2_exact(s1x, s1y, s1z, p[d][j].x, p[d][j].y, p[d][j].z));
+                    if (two) nm = fminf(nm, d2_exact(s2x, s2y, s2z, p[d][j].x, p[d][j].y, p[d][j].z));
                     if (nm < m[d][j]) {
                         if (RES) smin[(warp * 32 + Ls[d]) * BS + j * 32 + lane] = nm;
                         else M[(Ls[d] * FC_NW + gw) * BS + j * 32 + lane] = nm;
                     }
-                    const unsigned bits = __float_as_uint(nm);  // nm >= 0: the bit pattern is order preserving
-                    const unsigned nid = 0xffffffffu - __float_as_uint(p[d][j].w);
-                    if (bits > bb || (bits == bb && nid > bn)) { bb = bits; bn = nid; bx = p[d][j].x; by = p[d][j].y; bz = p[d][j].z; }
+                    // nm >= 0: the bit pattern is order preserving
+                    fc_merge(t, __float_as_uint(nm), 0xffffffffu - __float_as_uint(p[d][j].w), p[d][j].x, p[d][j].y, p[d][j].z);
                 }
-                if (bb > cb || (bb == cb && bn > cn)) { cb = bb; cn = bn; cx = bx; cy = by; cz = bz; }
+                fc_merge(c, t.b, t.n, t.x, t.y, t.z);
+                c.b2 = max(c.b2, t.b2);
                 if (!RES) {  // tiles in L2: the bucket's new maximum now, while its points are in registers
-                    uint4 w;
-                    const unsigned tb = fc_argmax(&sh.tmp[tog][warp], bb, bn, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz), w);
+                    fc_bucket(&sh.tmp[tog][warp], t, lane == Ls[d], maxbits, max2bits, argidx, ax, ay, az);
                     tog ^= 1;
-                    if (lane == Ls[d]) {
-                        maxbits = tb; argidx = 0xffffffffu - w.x;
-                        ax = __uint_as_float(w.y); ay = __uint_as_float(w.z); az = __uint_as_float(w.w);
-                    }
                 }
             }
         }
         FC_TICK(1);
-        fc_publish(sh, k, warp, lane, (k & 1) ? ra[1] : ra[0], (k & 1) ? rb[1] : rb[0], cb, cn, cx, cy, cz);
+        fc_publish(sh, r, warp, lane, (r & 1) ? ra[1] : ra[0], (r & 1) ? rb[1] : rb[0], c);
         FC_TICK(3);
         // ---- phase B, in the shadow of the exchange: the touched buckets' new maxima, for their owners ----
         if (RES) {
@@ -356,41 +426,42 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
             while (mask) {
                 const int L = 31 - __clz(mask);
                 mask &= ~(1u << L);
-                unsigned bb = 0u, bn = 0u;
-                float bx = 0.f, by = 0.f, bz = 0.f;
+                FcCand t;
+                t.b = t.n = t.b2 = 0u; t.x = t.y = t.z = 0.f;
 #pragma unroll
                 for (int j = 0; j < PPL; ++j) {
                     const int o = (warp * 32 + L) * BS + j * 32 + lane;
                     const float4 q = spts[o];
-                    const unsigned bits = __float_as_uint(smin[o]);
-                    const unsigned nid = 0xffffffffu - __float_as_uint(q.w);
-                    if (bits > bb || (bits == bb && nid > bn)) { bb = bits; bn = nid; bx = q.x; by = q.y; bz = q.z; }
+                    fc_merge(t, __float_as_uint(smin[o]), 0xffffffffu - __float_as_uint(q.w), q.x, q.y, q.z);
                 }
-                uint4 w;
-                const unsigned tb = fc_argmax(&sh.tmp[tog][warp], bb, bn, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz), w);
+                fc_bucket(&sh.tmp[tog][warp], t, lane == L, maxbits, max2bits, argidx, ax, ay, az);
                 tog ^= 1;
-                if (lane == L) {
-                    maxbits = tb; argidx = 0xffffffffu - w.x;
-                    ax = __uint_as_float(w.y); ay = __uint_as_float(w.z); az = __uint_as_float(w.w);
-                }
             }
         }
-        // ---- the cluster-wide winner ----
+        // ---- the round's result: one pick, or two ----
         FC_TICK(4);
-        unsigned sel;
-        fc_collect(sh, k, warp, lane, tid == 0, sel, sx, sy, sz);
+        FcPick o;
+        fc_collect(sh, r, warp, lane, tid == 0, k + 1 < kn, o);
         FC_TICK(5);
-        if (gw == 0) {  // one store per lane
-            if (lane == 0 && idx64) idx64[ob + k] = (int64_t)sel;
-            if (lane == 1 && idx32) idx32[ob + k] = (int32_t)sel;
-            if (lane == 2 && new_xyz4) new_xyz4[ob + k] = make_float4(sx, sy, sz, 0.f);
-            if (lane == 3 && new_pad) new_pad[ob + k] = 0;
+        if (gw == 0) {
+            fc_emit(ob + k, o.sel1, o.x1, o.y1, o.z1, lane, idx64, idx32, new_xyz4, new_pad);
+            if (o.two) fc_emit(ob + k + 1, o.sel2, o.x2, o.y2, o.z2, lane, idx64, idx32, new_xyz4, new_pad);
         }
+        s1x = o.x1; s1y = o.y1; s1z = o.z1;
+        s2x = o.x2; s2y = o.y2; s2z = o.z2;
+        two = o.two;
+        k += two ? 2 : 1;
+#ifdef DPM_FC_PROFILE
+        ++rounds;
+#endif
     }
 #ifdef DPM_FC_PROFILE
     if (lane == 0 && b == 0)
         for (int i = 0; i < 8; ++i) atomicAdd(&fc_prof[i], (unsigned long long)pacc[i]);
-    if (writer && b == 0) atomicAdd(&fc_prof[8], (unsigned long long)(kn - 1));
+    if (tid == 0 && rank == 0 && b == 0) {
+        atomicAdd(&fc_prof[8], (unsigned long long)(kn - 1));
+        atomicAdd(&fc_prof[9], (unsigned long long)rounds);
+    }
 #endif
     if (rank == 0) {
         for (int k = kn + tid; k < K; k += FC_T) {  // K > len: idx -1, zero rows, padded
@@ -420,7 +491,6 @@ fps_brute_cluster_kernel(const float4 *__restrict__ xyz4, int N, const int *__re
     const int kn = min(len, K);
     const float4 *pts = xyz4 + (size_t)b * N;
     const size_t ob = (size_t)b * K;
-    const bool writer = rank == 0 && tid == 0;
     fc_setup(sh, tid);
     unsigned ra[2], rb[2];
     fc_remote(sh, gw, lane, ra, rb);
@@ -437,45 +507,37 @@ fps_brute_cluster_kernel(const float4 *__restrict__ xyz4, int N, const int *__re
         }
         x[j] = p.x; y[j] = p.y; z[j] = p.z;
     }
-    float sx = 0.f, sy = 0.f, sz = 0.f;
+    float s1x = 0.f, s1y = 0.f, s1z = 0.f, s2x = 0.f, s2y = 0.f, s2z = 0.f;
+    bool two = false;
     if (len > 0) {
         const float4 p0 = pts[0];
-        sx = p0.x; sy = p0.y; sz = p0.z;
+        s1x = p0.x; s1y = p0.y; s1z = p0.z;
     }
-    if (writer && kn > 0) {
-        if (idx64) idx64[ob] = 0;
-        if (idx32) idx32[ob] = 0;
-        if (new_xyz4) new_xyz4[ob] = make_float4(sx, sy, sz, 0.f);
-        if (new_pad) new_pad[ob] = 0;
-    }
+    if (gw == 0 && kn > 0) fc_emit(ob, 0u, s1x, s1y, s1z, lane, idx64, idx32, new_xyz4, new_pad);
     fc_cluster_sync();
 
-    for (int k = 1; k < kn; ++k) {
-        float bm = 0.f;
+    int r = 1;
+    for (int k = 1; k < kn; ++r) {
+        FcCand c;
+        c.b = c.n = c.b2 = 0u; c.x = c.y = c.z = 0.f;
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            m[j] = fminf(m[j], d2_exact(sx, sy, sz, x[j], y[j], z[j]));
-            bm = fmaxf(bm, m[j]);
+        for (int j = P - 1; j >= 0; --j) {  // descending j: among this thread's ties the lowest index is merged last and wins
+            m[j] = fminf(m[j], d2_exact(s1x, s1y, s1z, x[j], y[j], z[j]));
+            if (two) m[j] = fminf(m[j], d2_exact(s2x, s2y, s2z, x[j], y[j], z[j]));
+            // m >= 0: the bit pattern is order preserving; tie key = ~index (never 0: index < 2^31)
+            fc_merge(c, __float_as_uint(m[j]), 0xffffffffu - (unsigned)(j * (FC_NW * 32) + gw * 32 + lane), x[j], y[j], z[j]);
         }
-        int jj = 0;
-#pragma unroll
-        for (int j = P - 1; j >= 0; --j)
-            if (m[j] == bm) jj = j;  // lowest j = lowest index among this thread's ties
-        float px = x[0], py = y[0], pz = z[0];
-#pragma unroll
-        for (int j = 1; j < P; ++j)
-            if (jj == j) { px = x[j]; py = y[j]; pz = z[j]; }
-        // bm >= 0: the bit pattern is order preserving; tie key = ~index (never 0: index < 2^31)
-        const unsigned nid = 0xffffffffu - (unsigned)(jj * (FC_NW * 32) + gw * 32 + lane);
-        fc_publish(sh, k, warp, lane, (k & 1) ? ra[1] : ra[0], (k & 1) ? rb[1] : rb[0], __float_as_uint(bm), nid, px, py, pz);
-        unsigned sel;
-        fc_collect(sh, k, warp, lane, tid == 0, sel, sx, sy, sz);
-        if (gw == 0) {  // one store per lane
-            if (lane == 0 && idx64) idx64[ob + k] = (int64_t)sel;
-            if (lane == 1 && idx32) idx32[ob + k] = (int32_t)sel;
-            if (lane == 2 && new_xyz4) new_xyz4[ob + k] = make_float4(sx, sy, sz, 0.f);
-            if (lane == 3 && new_pad) new_pad[ob + k] = 0;
+        fc_publish(sh, r, warp, lane, (r & 1) ? ra[1] : ra[0], (r & 1) ? rb[1] : rb[0], c);
+        FcPick o;
+        fc_collect(sh, r, warp, lane, tid == 0, k + 1 < kn, o);
+        if (gw == 0) {
+            fc_emit(ob + k, o.sel1, o.x1, o.y1, o.z1, lane, idx64, idx32, new_xyz4, new_pad);
+            if (o.two) fc_emit(ob + k + 1, o.sel2, o.x2, o.y2, o.z2, lane, idx64, idx32, new_xyz4, new_pad);
         }
+        s1x = o.x1; s1y = o.y1; s1z = o.z1;
+        s2x = o.x2; s2y = o.y2; s2z = o.z2;
+        two = o.two;
+        k += two ? 2 : 1;
     }
     if (rank == 0) {
         for (int k = kn + tid; k < K; k += FC_T) {

@@ -25,6 +25,6 @@ for kind, n, k in (("kitti", 65536, 4096), ("cube", 65536, 4096), ("kitti", 1638
     lib.dpm_debug_fc_profile(buf, 1)
     picks = buf[8]
     tot = sum(buf[i] for i in range(8)) / 32.0 / max(picks, 1)
-    print(f"{kind} N={n} K={k}: {tot:.0f} cycles per pick per warp (avg over 32 warps)")
+    print(f"{kind} N={n} K={k}: {tot:.0f} cycles per pick per warp (avg over 32 warps); {picks} picks in {buf[9]} rounds")
     for i in range(8):
         print(f"   {names[i]:28s} {buf[i] / 32.0 / max(picks, 1):8.1f}")
