@@ -113,8 +113,9 @@ def check(rc: int, what: str = ""):
         raise exc(f"libdpm_b200 {what}: {kind} error: {msg}")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """raw handle of torch's current stream ON `device` (default: the current device)"""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def require_cuda(*tensors):
@@ -129,18 +130,36 @@ def ptr(t):
 
 
 class _Workspaces(threading.local):
-    """One growable scratch buffer per (host thread, device, slot)."""
+    """One growable scratch buffer per (host thread, device, slot); a slot is "<module><stream handle>", so calls on
+    different streams never share scratch.  At most MAX_SLOTS buffers are kept per thread (least recently used goes
+    first: a process that rotates over torch's stream pool does not accumulate them) and `release()` drops them all;
+    a dropped buffer goes back to torch's caching allocator, which keeps it alive for the kernels already queued on
+    the stream it was last used on (record_stream)."""
+    MAX_SLOTS = 24
 
     def __init__(self):
-        self.buf = {}
+        self.buf = {}  # insertion-ordered: least recently used first
 
     def get(self, device, nbytes: int, slot: str = "default") -> torch.Tensor:
         key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
-        b = self.buf.get(key)
+        b = self.buf.pop(key, None)
         if b is None or b.numel() < nbytes:
-            b = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
-            self.buf[key] = b
+            b = torch.empty(int(nbytes) + (int(nbytes) >> 4) + 4096, dtype=torch.uint8, device=device)
+            b.record_stream(torch.cuda.current_stream(device))
+        self.buf[key] = b
+        while len(self.buf) > self.MAX_SLOTS:
+            self.buf.pop(next(iter(self.buf)))
         return b
+
+    def release(self, device=None) -> int:
+        """drop this thread's scratch buffers (of one device, or all); returns the bytes handed back"""
+        idx = None if device is None else torch.device(device).index
+        keys = [k for k in self.buf if idx is None or k[0] == idx]
+        freed = sum(self.buf.pop(k).numel() for k in keys)
+        return freed
+
+    def held_bytes(self) -> int:
+        return sum(b.numel() for b in self.buf.values())
 
 
 workspaces = _Workspaces()

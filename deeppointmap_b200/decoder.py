@@ -173,7 +173,7 @@ class Decoder(nn.Module):
         nb = lib.dpm_registration_workspace_bytes(ctypes.byref(self._desc), P, M, N, k)
         if nb == 0:
             _C.check(-1, "registration workspace")
-        ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr()}")
+        ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr(dev)}")
         with torch.cuda.device(dev):
             rc = lib.dpm_registration_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(), P, M,
                                               N, k, result.data_ptr(), conf.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -219,7 +219,7 @@ class Decoder(nn.Module):
         warr, nw = self._weights(dev)
         prob = torch.empty((P,), dtype=torch.float32, device=dev)
         nb = lib.dpm_loop_detection_workspace_bytes(ctypes.byref(self._desc), P, M, N)
-        ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr()}")
+        ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr(dev)}")
         with torch.cuda.device(dev):
             rc = lib.dpm_loop_detection_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(), P, M,
                                                 N, prob.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr())

@@ -185,6 +185,10 @@ class Encoder(nn.Module):
     # ---- forward -----------------------------------------------------------------------------
     def _run(self, points: Tensor, points_padding: Optional[Tensor], want_desc: bool, coor_scale: float,
              desc_out: Optional[Tensor] = None):
+        if self.training and torch.is_grad_enabled():
+            # pipeline/train.py would otherwise get detached features without any notice
+            raise NotImplementedError("deeppointmap_b200.Encoder is inference-only (no autograd path): call .eval() "
+                                      "and / or run under torch.no_grad()")
         _C.require_cuda(points, points_padding)
         if points.dim() != 3 or points.shape[1] < 3:
             raise ValueError("points must be (B, C>=3, N)")
@@ -219,7 +223,7 @@ class Encoder(nn.Module):
         nb = lib.dpm_encoder_workspace_bytes(ctypes.byref(self._desc), B, N)
         if nb == 0:
             _C.check(-1, "encoder workspace")
-        ws = _C.workspaces.get(dev, nb, f"enc{_C.stream_ptr()}")
+        ws = _C.workspaces.get(dev, nb, f"enc{_C.stream_ptr(dev)}")
         with torch.cuda.device(dev):
             rc = lib.dpm_encoder_forward(ctypes.byref(self._desc), warr, nw, pts.data_ptr(), C, _C.ptr(pad), B, N,
                                          coor.data_ptr(), fea.data_ptr(), opad.data_ptr(), _C.ptr(desc),

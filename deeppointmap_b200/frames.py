@@ -47,6 +47,16 @@ class FrameParallel:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    def _ag(self, out: Tensor, x: Tensor) -> None:
+        """all_gather_into_tensor; a gloo group (CPU tests, or several ranks sharing one GPU) is fed through host
+        copies, NCCL takes the device tensors as they are"""
+        if x.is_cuda and dist.get_backend(self.group) == "gloo":
+            h = torch.empty(out.shape, dtype=out.dtype)
+            dist.all_gather_into_tensor(h, x.cpu(), group=self.group)
+            out.copy_(h)
+        else:
+            dist.all_gather_into_tensor(out, x, group=self.group)
+
     def _all_gather_padded(self, x: Tensor, sizes: List[int]) -> Tensor:
         """all-gather of per-rank blocks with different leading sizes (padded to the largest)."""
         if self.world == 1:
@@ -55,14 +65,19 @@ class FrameParallel:
         buf = x.new_zeros((m,) + tuple(x.shape[1:]))
         buf[: x.shape[0]] = x
         out = x.new_empty((self.world * m,) + tuple(x.shape[1:]))
-        dist.all_gather_into_tensor(out, buf, group=self.group)
+        self._ag(out, buf)
+        if len(set(sizes)) == 1:
+            return out
         return torch.cat([out[r * m: r * m + s] for r, s in enumerate(sizes)], dim=0)
 
     @torch.no_grad()
-    def odometry(self, local_points: Tensor, n_frames: int, prev_desc: Optional[Tensor] = None):
+    def odometry(self, local_points: Tensor, n_frames: int, prev_desc: Optional[Tensor] = None,
+                 desc_shape: Optional[Tuple[int, int]] = None):
         """local_points: this rank's block (shard(n_frames, world, rank)) of the global batch.
         Returns (poses (n_frames, REG_STRIDE) for the pairs (i-1 -> i), i = 0 pairs with
-        `prev_desc` (the last frame of the previous batch) or is zero-filled; local descriptors)."""
+        `prev_desc` (the last frame of the previous batch) or is zero-filled; local descriptors).
+        desc_shape = (Cd, S) of a descriptor set when the caller knows it: skips the one collective (and host
+        sync) that otherwise lets ranks without frames learn it."""
         start, stop = shard(n_frames, self.world, self.rank)
         f = stop - start
         if local_points.shape[0] != f:
@@ -72,15 +87,20 @@ class FrameParallel:
         # boundary exchange: last descriptor of every rank
         if self.world > 1:
             # every rank must contribute the same shape: learn it from whoever has frames
-            if desc is not None:
-                shape = torch.tensor(list(desc.shape[1:]), device=local_points.device, dtype=torch.int64)
+            if desc_shape is not None:
+                cd, s = int(desc_shape[0]), int(desc_shape[1])
             else:
-                shape = torch.zeros(2, device=local_points.device, dtype=torch.int64)
-            dist.all_reduce(shape, op=dist.ReduceOp.MAX, group=self.group)
-            cd, s = int(shape[0]), int(shape[1])
+                if desc is not None:
+                    shape = torch.tensor(list(desc.shape[1:]), dtype=torch.int64)
+                else:
+                    shape = torch.zeros(2, dtype=torch.int64)
+                if dist.get_backend(self.group) != "gloo":
+                    shape = shape.to(local_points.device)
+                dist.all_reduce(shape, op=dist.ReduceOp.MAX, group=self.group)
+                cd, s = int(shape[0]), int(shape[1])
             last = desc[-1:] if desc is not None else torch.zeros((1, cd, s), device=local_points.device)
             lasts = torch.empty((self.world, cd, s), dtype=last.dtype, device=last.device)
-            dist.all_gather_into_tensor(lasts, last.contiguous(), group=self.group)
+            self._ag(lasts, last.contiguous())
         else:
             lasts = None
         poses = torch.zeros((f, REG_STRIDE), dtype=torch.float32, device=local_points.device)

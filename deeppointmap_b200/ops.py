@@ -31,7 +31,7 @@ def _lengths(lengths, B: int, P: int, device):
 
 
 def _ws(device, nbytes):
-    return _C.workspaces.get(device, nbytes, f"ops{_C.stream_ptr()}")
+    return _C.workspaces.get(device, nbytes, f"ops{_C.stream_ptr(device)}")
 
 
 def set_fps_mode(mode: int = 0) -> None:

@@ -206,3 +206,39 @@ def test_map_tile_and_scan_to_map_registration(cfg, checkpoint):
     assert float((T.flatten().cpu().double() - want_rel[:3, 3]).norm()) < 0.6
     Rw, Tw, cw, rw = M.registration_forward(checkpoint["decoder"], cfg, desc[4].cpu(), tile.cpu(), 0.5)
     assert float((R.cpu() - Rw).abs().max()) < 1e-4 and float((T.cpu() - Tw).abs().max()) < 1e-4 * max(1.0, float(Tw.abs().max()))
+
+
+def _map_of(blocks, seeds):
+    """a map tile the way PoseGraph.__global_mapping concatenates key-point sets (pose_graph.py:373-409)"""
+    out = []
+    for i, (b, s) in enumerate(zip(blocks, seeds)):
+        out.append(_moved(b, yaw_deg=0.7 * i, t=(1.5 * i, 0.2 * i, 0.0), noise=0.01, seed=s))
+    return torch.cat(out, dim=1)
+
+
+@pytest.mark.parametrize("m_blocks,n_blocks", [(16, 1), (16, 16), (1, 16), (7, 3)])
+def test_registration_caller_sizes(cfg, checkpoint, golden_sample, m_blocks, n_blocks):
+    """The sizes the SLAM callers use: graph_search(max_k=16) bounds a map tile at 16 x 256 = 4096 descriptors
+    (pose_graph.py:513); scan-to-map is M=4096 vs N=256 (mapping.py:153), map-to-map M=N=4096
+    (loop_closure.py:240) -> k = 1088 / 2048 pairs, 2k = 4096 Kabsch rows at the limit of the kernels."""
+    dec = _dec(cfg, checkpoint["decoder"])
+    d0, d1 = torch.from_numpy(golden_sample["desc0"]), torch.from_numpy(golden_sample["desc1"])
+    src = _map_of([d0 if i % 2 == 0 else d1 for i in range(m_blocks)], range(100, 100 + m_blocks)) if m_blocks > 1 else d0
+    dst = _map_of([d1 if i % 2 == 0 else d0 for i in range(n_blocks)], range(200, 200 + n_blocks)) if n_blocks > 1 else d1
+    assert src.shape[1] == 256 * m_blocks and dst.shape[1] == 256 * n_blocks
+    _check_registration(dec, checkpoint["decoder"], cfg, src, dst)
+
+
+@pytest.mark.parametrize("C,Ms,Ns", [(8, 256, 256), (5, 256, 192), (13, 100, 256)])
+def test_loop_detection_batched_unsaturated(cfg, C, Ms, Ns):
+    """loop_closure.py:171: C candidates in one call.  Random weights keep the logits away from the sigmoid's flat
+    ends, so the 1e-4 bar is a real check of the whole stack (the trained head saturates at 0.999999)."""
+    sd = M.random_weights(M.decoder_shapes(cfg), seed=11)
+    dec = _dec(cfg, sd)
+    S = _descs(31, Ms, P=C)
+    D = torch.stack([_moved(S[i], seed=i)[:, :Ns] if Ns <= Ms else _descs(50 + i, Ns) for i in range(C)])
+    want = M.loop_detection_forward(sd, cfg, S, D)
+    got = dec.loop_detection_forward(S.to(DEV), D.to(DEV))
+    assert got.shape == (C,)
+    assert float(want.min()) > 1e-3 and float(want.max()) < 1 - 1e-3, "test data saturates the sigmoid"
+    assert (got.cpu() - want).abs().max() < TOL

@@ -86,3 +86,26 @@ def test_synthetic_cloud_is_deterministic():
     assert r.min() >= 1.0 - 1e-3 and r.max() <= 60.0 + 1e-3
     c = data.kitti_shape_cloud(0, 65536)
     assert c.shape == (3, 65536)
+
+
+def test_encoder_refuses_training_with_grad(cfg):
+    """the drop-in has no autograd path; pipeline/train.py must get an error, not detached features."""
+    from deeppointmap_b200 import Encoder
+    e = Encoder(cfg).train()
+    with pytest.raises(NotImplementedError):
+        e(torch.zeros(1, 3, 64), torch.zeros(1, 64, dtype=torch.bool))
+    with torch.no_grad(), pytest.raises(RuntimeError):  # past the mode check: CPU tensors are refused (no fallback)
+        e(torch.zeros(1, 3, 64), torch.zeros(1, 64, dtype=torch.bool))
+
+
+def test_workspace_cache_is_bounded_and_releasable():
+    from deeppointmap_b200 import _C
+    ws = _C._Workspaces()
+    ws.MAX_SLOTS = 3
+    dev = torch.device("cpu")
+    for i in range(5):
+        ws.buf[(0, f"s{i}")] = torch.empty(10, dtype=torch.uint8)
+        while len(ws.buf) > ws.MAX_SLOTS:
+            ws.buf.pop(next(iter(ws.buf)))
+    assert list(k[1] for k in ws.buf) == ["s2", "s3", "s4"] and ws.held_bytes() == 30
+    assert ws.release() == 30 and ws.held_bytes() == 0

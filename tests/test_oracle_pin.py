@@ -75,6 +75,8 @@ def test_fps_matches_reference_sampler(reference, n, k, valid):
     got = torch.gather(pts, 1, idx.clamp(min=0)[..., None].expand(-1, -1, 3))
     got[idx < 0] = 0
     assert torch.equal(got, ref_pts)
+    # the pure-torch restatement bench.py's reference_gpu leg runs on the device
+    assert torch.equal(M.fps_torch(pts, (~pad).sum(1), k), idx)
 
 
 @needs_ref
