@@ -19,11 +19,10 @@ needs_ref = pytest.mark.skipif(not HAS_REF, reason="/root/reference not present 
 
 @pytest.fixture(scope="module")
 def reference():
-    sys.path[:0] = [os.path.join(ROOT, "deeppointmap_b200", "compat"), REF]
-    # compat/ also holds our pytorch3d.ops package; the pin needs the reference's own pure-torch
-    # fallbacks (CPU), so make `import pytorch3d` fail while its modules are imported and built
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "pytorch3d" or k.startswith("pytorch3d.")}
-    sys.modules["pytorch3d"] = None
+    from oracle import ref_loader
+    saved = {k: v for k, v in sys.modules.items() if k == "pytorch3d" or k.startswith("pytorch3d.")}
+    # the pin needs the reference's own pure-torch fallbacks (CPU): `import pytorch3d` fails while its modules load
+    ref_loader.activate("fallback")
     import yaml
     from easydict import EasyDict
     from network.encoder.encoder import Encoder
@@ -332,6 +331,7 @@ def test_map_tile_matches_reference_posegraph():
     saved = sys.modules.get("readerwriterlock")
     sys.modules["readerwriterlock"] = rw
     sys.path[:0] = [os.path.join(ROOT, "deeppointmap_b200", "compat"), REF]
+    sys.path.append(os.path.join(ROOT, "deeppointmap_b200", "compat_shims"))
     try:
         PG = importlib.import_module("system.modules.pose_graph")
     finally:

@@ -14,10 +14,11 @@ from oracle import index_ops as IO
 HAS_REF = os.path.isdir(os.path.join(REF, "network"))
 COMPAT = os.path.join(ROOT, "deeppointmap_b200", "compat")
 DROPIN = os.path.join(ROOT, "deeppointmap_b200", "dropin")
+SHIMS = os.path.join(ROOT, "deeppointmap_b200", "compat_shims")  # LAST on the path: installed packages win
 
 
 def _run(code: str) -> str:
-    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, DROPIN, COMPAT, REF]))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, DROPIN, COMPAT, REF, SHIMS]))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     return r.stdout
