@@ -89,7 +89,12 @@ __device__ __forceinline__ void mma_tf32_16n8k8(float (&c)[4], const unsigned (&
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(AT_T, 512 / AT_T)
+// LONG (key ranges of more than 512 rows, i.e. map tiles): the tensor core's fp32 accumulate TRUNCATES, a bias
+// of ~2^-24 per k-step that is invisible over the 32 k-steps of a 256-key set but reaches 2e-5 over the 512
+// k-steps of a 4096-key map tile (measured against fp64).  There every 64-key tile accumulates P V into fresh
+// registers and is folded into the running output with one IEEE fma per element.
+template <bool LONG>
+__global__ void __launch_bounds__(AT_T, LONG ? 1 : 512 / AT_T)
 attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__ Kp, int ldk,
                     const float *__restrict__ Vp, int ldv, float *__restrict__ O, int ldo, const int *__restrict__ prob,
                     int M, int N, int mode) {
@@ -198,10 +203,18 @@ attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restric
         const float corr0 = expf(m0 - mn0), corr1 = expf(m1 - mn1);
         m0 = mn0; m1 = mn1;
         l0 *= corr0; l1 *= corr1;
+        float th[LONG ? 4 : 1][4], tx[LONG ? 4 : 1][4];  // LONG: this tile's P V (hi*hi / cross terms)
+        if (LONG) {
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            oh[d][0] *= corr0; oh[d][1] *= corr0; oh[d][2] *= corr1; oh[d][3] *= corr1;
-            ox[d][0] *= corr0; ox[d][1] *= corr0; ox[d][2] *= corr1; ox[d][3] *= corr1;
+            for (int d = 0; d < (LONG ? 4 : 1); ++d)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { th[d][i] = 0.f; tx[d][i] = 0.f; }
+        } else {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                oh[d][0] *= corr0; oh[d][1] *= corr0; oh[d][2] *= corr1; oh[d][3] *= corr1;
+                ox[d][0] *= corr0; ox[d][1] *= corr0; ox[d][2] *= corr1; ox[d][3] *= corr1;
+            }
         }
         // ---- O += P V, 8 keys per k-step; k index t <-> key 2t, k index t+4 <-> key 2t+1 ----
 #pragma unroll
@@ -219,9 +232,24 @@ attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restric
             for (int d = 0; d < 4; ++d) {
                 const int o = (8 * j + 2 * t) * AT_LD + 8 * d + g;
                 const unsigned b0h = Vh[o], b1h = Vh[o + AT_LD], b0l = Vl[o], b1l = Vl[o + AT_LD];
-                mma_tf32_16n8k8(oh[d], ph, b0h, b1h);
-                mma_tf32_16n8k8(ox[d], ph, b0l, b1l);
-                mma_tf32_16n8k8(ox[d], pl, b0h, b1h);
+                if (LONG) {
+                    mma_tf32_16n8k8(th[LONG ? d : 0], ph, b0h, b1h);
+                    mma_tf32_16n8k8(tx[LONG ? d : 0], ph, b0l, b1l);
+                    mma_tf32_16n8k8(tx[LONG ? d : 0], pl, b0h, b1h);
+                } else {
+                    mma_tf32_16n8k8(oh[d], ph, b0h, b1h);
+                    mma_tf32_16n8k8(ox[d], ph, b0l, b1l);
+                    mma_tf32_16n8k8(ox[d], pl, b0h, b1h);
+                }
+            }
+        }
+        if (LONG) {
+#pragma unroll
+            for (int d = 0; d < (LONG ? 4 : 1); ++d) {
+                oh[d][0] = fmaf(oh[d][0], corr0, th[d][0] + tx[d][0]);
+                oh[d][1] = fmaf(oh[d][1], corr0, th[d][1] + tx[d][1]);
+                oh[d][2] = fmaf(oh[d][2], corr1, th[d][2] + tx[d][2]);
+                oh[d][3] = fmaf(oh[d][3], corr1, th[d][3] + tx[d][3]);
             }
         }
     }
@@ -246,7 +274,11 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
     if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
     dim3 grid((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
-    attention_tc_kernel<<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
+    // the longest key range of the launch decides (prob == nullptr: the two sides of the pairs; else the caller's table,
+    // which this host code cannot read: the accurate variant then)
+    const bool lng = prob ? true : (M > 512 || N > 512);
+    if (lng) attention_tc_kernel<true><<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
+    else attention_tc_kernel<false><<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
     DPM_CHECK_LAUNCH("attention", st);
     return DPM_OK;
 }

@@ -98,7 +98,7 @@ def test_kabsch_vs_oracle():
         assert torch.equal(conf[p, :int(iw.sum())], w[p, :n][iw])
 
 
-def _check_registration(dec, sd, cfg, src, dst, num_sample=0.5):
+def _check_registration(dec, sd, cfg, src, dst, num_sample=0.5, conf_vs_fp64=False):
     tr = {}
     Rw, Tw, cw, rw = M.registration_forward(sd, cfg, src, dst, num_sample, trace=tr)
     R, T, c, r = dec.registration_forward(src.to(DEV), dst.to(DEV), num_sample=num_sample)
@@ -106,7 +106,20 @@ def _check_registration(dec, sd, cfg, src, dst, num_sample=0.5):
     assert c.shape == cw.shape, f"inlier count {c.shape} vs oracle {cw.shape}"
     assert (R.cpu() - Rw).abs().max() < TOL
     assert (T.cpu() - Tw).abs().max() < TOL * max(1.0, float(Tw.abs().max()))
-    assert (c.cpu() - cw).abs().max() < TOL
+    if conf_vs_fp64:
+        # A confidence is exp(2 s / tau - lse_row - lse_col) with tau = 0.1: its condition number w.r.t. the cosine s
+        # is 20, and with thousands of map descriptors the fp32 reference itself sits 3e-5 .. 1.5e-4 away from an
+        # fp64 evaluation of the same formula (tools/probe_conf.py).  The bar at map sizes is therefore "as close to
+        # the fp64 truth as the fp32 reference is", not a number below the reference's own rounding noise.
+        sd64 = {k: v.double() for k, v in sd.items()}
+        s6, d6, _, _ = M.attention_forward(sd64, cfg, src[None].double(), dst[None].double())
+        P6 = M.pairing(sd64, cfg, s6, d6, num_sample)[3]
+        c64 = P6[tr["src_index"], tr["dst_index"]].repeat(2)[tr["keep"]][tr["inlier"]]
+        err_ref = float((cw.double() - c64).abs().max())
+        err_gpu = float((c.cpu().double() - c64).abs().max())
+        assert err_gpu < max(TOL, 1.5 * err_ref), f"confidence vs fp64: gpu {err_gpu:.2e}, fp32 reference {err_ref:.2e}"
+    else:
+        assert (c.cpu() - cw).abs().max() < TOL
     assert abs(r - rw) < TOL * max(1.0, rw)
     return R, T, c, r
 
@@ -226,7 +239,7 @@ def test_registration_caller_sizes(cfg, checkpoint, golden_sample, m_blocks, n_b
     src = _map_of([d0 if i % 2 == 0 else d1 for i in range(m_blocks)], range(100, 100 + m_blocks)) if m_blocks > 1 else d0
     dst = _map_of([d1 if i % 2 == 0 else d0 for i in range(n_blocks)], range(200, 200 + n_blocks)) if n_blocks > 1 else d1
     assert src.shape[1] == 256 * m_blocks and dst.shape[1] == 256 * n_blocks
-    _check_registration(dec, checkpoint["decoder"], cfg, src, dst)
+    _check_registration(dec, checkpoint["decoder"], cfg, src, dst, conf_vs_fp64=True)
 
 
 @pytest.mark.parametrize("C,Ms,Ns", [(8, 256, 256), (5, 256, 192), (13, 100, 256)])
