@@ -82,6 +82,21 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// in-place bitonic sort (descending) of n = 2^m 64-bit keys in shared memory by all threads of the block
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long *s, int n, int tid, int nthreads) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (n >> 1); i += nthreads) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long a = s[lo], b = s[hi];
+                if (desc ? (a < b) : (a > b)) { s[lo] = b; s[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -175,6 +190,11 @@ int group_from_xyz_launch(const float *Wsa, int ldw, const float *bias, const fl
                           float4 *comp, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *gamma,
                           const float *beta, float radius, float *out, int B, int N, int S, int K, int Cout,
                           cudaStream_t st);
+// pairing.cu: dual softmax + global top-k of the similarity matrices, three launches
+constexpr int PAIR_MAXK = 4096;
+size_t pairing_ws_bytes(int P);
+int pairing_launch(float *S, int P, int M, int N, float tau, int k, float2 *rs, float2 *cs, void *ws, int32_t *si,
+                   int32_t *di, float *conf, cudaStream_t st);
 int fp_interp_launch(const float4 *xyz1, const float4 *xyz2, const float *fea1, const float *fea2,
                      const uint8_t *pad2, float *out, int B, int N, int S, int C1, int C2, cudaStream_t st);
 

@@ -296,171 +296,6 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(float *__restrict__ X,
     for (int c = lane; c < C; c += 32) x[c] = x[c] / nrm;
 }
 
-// per-row (max, sum exp) of S/tau; S (P, M, N)
-__global__ void __launch_bounds__(256)
-row_stats_kernel(const float *__restrict__ S, int rows, int N, float tau, float2 *__restrict__ stats) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const float *s = S + (size_t)row * N;
-    float mx = -__int_as_float(0x7f800000);
-    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, __fdiv_rn(s[j], tau));
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < N; j += 32) sum += expf(__fdiv_rn(s[j], tau) - mx);
-    sum = warp_sum(sum);
-    if (lane == 0) stats[row] = make_float2(mx, sum);
-}
-
-// per-column stats: block = 32 columns x 8 row-slices
-__global__ void __launch_bounds__(256)
-col_stats_kernel(const float *__restrict__ S, int M, int N, float tau, float2 *__restrict__ stats) {
-    __shared__ float smx[8][32], ssum[8][32];
-    const int p = blockIdx.y;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + tx;
-    const float *s = S + (size_t)p * M * N;
-    float mx = -__int_as_float(0x7f800000), sum = 0.f;
-    if (j < N) {
-        for (int i = ty; i < M; i += 8) mx = fmaxf(mx, __fdiv_rn(s[(size_t)i * N + j], tau));
-    }
-    smx[ty][tx] = mx;
-    __syncthreads();
-    float gm = smx[0][tx];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) gm = fmaxf(gm, smx[w][tx]);
-    if (j < N) {
-        for (int i = ty; i < M; i += 8) sum += expf(__fdiv_rn(s[(size_t)i * N + j], tau) - gm);
-    }
-    ssum[ty][tx] = sum;
-    __syncthreads();
-    if (ty == 0 && j < N) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += ssum[w][tx];
-        stats[(size_t)p * N + j] = make_float2(gm, t);
-    }
-}
-
-// P = softmax_row * softmax_col, in place over S
-__global__ void __launch_bounds__(256)
-dual_softmax_kernel(float *__restrict__ S, int M, int N, float tau, const float2 *__restrict__ rs,
-                    const float2 *__restrict__ cs, long long total) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const long long row = t / N;
-    const int j = (int)(t % N);
-    const int p = (int)(row / M);
-    const float x = __fdiv_rn(S[t], tau);
-    const float2 r = rs[row], c = cs[(size_t)p * N + j];
-    S[t] = (expf(x - r.x) / r.y) * (expf(x - c.x) / c.y);
-}
-
-__device__ __forceinline__ void bitonic_sort_desc(unsigned long long *s, int n, int tid, int nthreads) {
-    for (int size = 2; size <= n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = tid; i < (n >> 1); i += nthreads) {
-                const int lo = 2 * i - (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool desc = (lo & size) == 0;
-                const unsigned long long a = s[lo], b = s[hi];
-                if (desc ? (a < b) : (a > b)) { s[lo] = b; s[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// top-k of the flattened (M*N) non-negative matrix; order = (value desc, flat index asc).
-// One CTA per pair: 4-pass radix select of the k-th largest bit pattern, ordered collection,
-// bitonic sort of the k winners.
-constexpr int TOPK_T = 1024;
-constexpr int TOPK_MAXK = 4096;
-
-__global__ void __launch_bounds__(TOPK_T)
-topk_kernel(const float *__restrict__ Pm, int MN, int N, int k, int kp2, int32_t *__restrict__ si,
-            int32_t *__restrict__ di, float *__restrict__ conf) {
-    extern __shared__ __align__(16) unsigned char tk_smem[];
-    unsigned long long *sel = reinterpret_cast<unsigned long long *>(tk_smem);  // kp2
-    int *hist = reinterpret_cast<int *>(sel + kp2);                             // 32 x 256 (per-warp)
-    __shared__ unsigned s_prefix;
-    __shared__ int s_remaining, s_ngreater, s_eqbase, s_wcnt[32];
-    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned *v = reinterpret_cast<const unsigned *>(Pm + (size_t)p * MN);
-    if (tid == 0) { s_prefix = 0u; s_remaining = k; s_ngreater = 0; s_eqbase = 0; }
-    for (int i = tid; i < kp2; i += TOPK_T) sel[i] = 0ull;
-    __syncthreads();
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int i = tid; i < 32 * 256; i += TOPK_T) hist[i] = 0;
-        __syncthreads();
-        const unsigned prefix = s_prefix;
-        for (int i0 = 0; i0 < MN; i0 += TOPK_T) {
-            const int i = i0 + tid;
-            const bool ok = i < MN && ((v[i] & himask) == prefix);
-            const unsigned digit = ok ? ((v[i] >> shift) & 255u) : 256u;
-            const unsigned peers = __match_any_sync(0xffffffffu, digit);
-            if (ok && lane == __ffs(peers) - 1) hist[warp * 256 + digit] += __popc(peers);
-            __syncwarp();
-        }
-        __syncthreads();
-        if (tid < 256) {
-            int t = 0;
-            for (int w = 0; w < 32; ++w) t += hist[w * 256 + tid];
-            hist[tid] = t;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int cum = 0, rem = s_remaining, d = 255;
-            for (; d > 0; --d) {
-                if (cum + hist[d] >= rem) break;
-                cum += hist[d];
-            }
-            s_prefix = prefix | ((unsigned)d << shift);
-            s_remaining = rem - cum;
-        }
-        __syncthreads();
-    }
-    const unsigned T = s_prefix;
-    const int need_eq = s_remaining;  // how many of the == T elements are taken (lowest indices)
-    for (int i0 = 0; i0 < MN; i0 += TOPK_T) {
-        const int i = i0 + tid;
-        const unsigned u = i < MN ? v[i] : 0u;
-        const bool gt = i < MN && u > T;
-        const bool eq = i < MN && u == T;
-        if (gt) {
-            const int pos = atomicAdd(&s_ngreater, 1);
-            sel[pos] = ((unsigned long long)u << 32) | (unsigned)(0xffffffffu - (unsigned)i);
-        }
-        if (__syncthreads_or(eq) && s_eqbase < need_eq) {
-            const unsigned bal = __ballot_sync(0xffffffffu, eq);
-            if (lane == 0) s_wcnt[warp] = __popc(bal);
-            __syncthreads();
-            int before = 0;
-            for (int w = 0; w < warp; ++w) before += s_wcnt[w];
-            const int rank = s_eqbase + before + __popc(bal & ((1u << lane) - 1u));
-            if (eq && rank < need_eq)
-                sel[k - need_eq + rank] = ((unsigned long long)u << 32) | (unsigned)(0xffffffffu - (unsigned)i);
-            __syncthreads();
-            if (tid == 0) {
-                int t = 0;
-                for (int w = 0; w < 32; ++w) t += s_wcnt[w];
-                s_eqbase += t;
-            }
-            __syncthreads();
-        }
-    }
-    __syncthreads();
-    bitonic_sort_desc(sel, kp2, tid, TOPK_T);
-    for (int r = tid; r < k; r += TOPK_T) {
-        const unsigned long long e = sel[r];
-        const unsigned flat = 0xffffffffu - (unsigned)e;
-        si[(size_t)p * k + r] = (int)(flat / (unsigned)N);
-        di[(size_t)p * k + r] = (int)(flat % (unsigned)N);
-        conf[(size_t)p * k + r] = __uint_as_float((unsigned)(e >> 32));
-    }
-}
-
 // rows of the offset head input: r < k: [F_src[i_r], F_dst[j_r]] ; k + r: [F_dst[j_r], F_src[i_r]]
 __global__ void __launch_bounds__(256)
 pair_gather_kernel(const float *__restrict__ F, int C, int M, int N, int k, const int32_t *__restrict__ si,
@@ -896,7 +731,7 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     const bool dry = a.dry;
     if (P <= 0 || M <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "registration: bad shape P=%d M=%d N=%d", P, M, N);
     if (k <= 0 || (long long)k > (long long)M * N) return fail(DPM_ERR_SHAPE, "registration: k=%d pairs out of range", k);
-    if (k > TOPK_MAXK || 2 * k > KAB_MAX) return fail(DPM_ERR_UNSUPPORTED, "registration: k=%d exceeds the limit %d", k, KAB_MAX / 2);
+    if (k > PAIR_MAXK || 2 * k > KAB_MAX) return fail(DPM_ERR_UNSUPPORTED, "registration: k=%d exceeds the limit %d", k, KAB_MAX / 2);
     DecW w;
     if (!dry) dec_bind(d, weights, w);
     const int C = d->model_channel, R = P * (M + N), K2 = 2 * k;
@@ -910,6 +745,7 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     float *S = a.get<float>((size_t)P * M * N);
     float2 *rs = a.get<float2>((size_t)P * M);
     float2 *cs = a.get<float2>((size_t)P * N);
+    void *pws = a.get<unsigned char>(pairing_ws_bytes(P));
     int32_t *si = a.get<int32_t>((size_t)P * k);
     int32_t *di = a.get<int32_t>((size_t)P * k);
     float *conf = a.get<float>((size_t)P * k);
@@ -934,25 +770,7 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     // S_p = A_src . A_dst^T
     DPM_TRY(linear_batched_launch(sim, C, (long long)(M + N) * C, sim + (size_t)M * C, C, (long long)(M + N) * C, nullptr,
                                   nullptr, 0, S, N, (long long)M * N, M, N, C, P, DPM_ACT_NONE, st));
-    row_stats_kernel<<<(P * M + 7) / 8, 256, 0, st>>>(S, P * M, N, d->tau, rs);
-    DPM_CHECK_LAUNCH("row_stats", st);
-    col_stats_kernel<<<dim3((N + 31) / 32, P, 1), 256, 0, st>>>(S, M, N, d->tau, cs);
-    DPM_CHECK_LAUNCH("col_stats", st);
-    const long long total = (long long)P * M * N;
-    dual_softmax_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, M, N, d->tau, rs, cs, total);
-    DPM_CHECK_LAUNCH("dual_softmax", st);
-    int kp2 = 2;
-    while (kp2 < k) kp2 <<= 1;
-    const size_t tk_smem = (size_t)kp2 * 8 + 32 * 256 * 4;
-    static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
-    const unsigned long long devbit = 1ull << (current_device() & 63);
-    if (!(configured & devbit)) {
-        DPM_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(TOPK_MAXK * 8 + 32 * 256 * 4)));
-        configured |= devbit;
-    }
-    topk_kernel<<<P, TOPK_T, tk_smem, st>>>(S, M * N, N, k, kp2, si, di, conf);
-    DPM_CHECK_LAUNCH("topk", st);
+    DPM_TRY(pairing_launch(S, P, M, N, d->tau, k, rs, cs, pws, si, di, conf, st));
     // offset head on [f_s;f_d] and [f_d;f_s]  (heads.py:22-42)
     pair_gather_kernel<<<dim3(K2, P, 1), 256, 0, st>>>(F, C, M, N, k, si, di, X);
     DPM_CHECK_LAUNCH("pair_gather", st);
