@@ -164,6 +164,7 @@ int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int 
                      const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
                      int act, cudaStream_t st);
 // per-call pre-split (hi/lo tf32) copies of the weights for the tensor-core path (gemm_tc.cu)
+size_t split_floats(int rows, int cols);  // floats of the hi + lo copies of a rows x cols weight
 void split_begin();
 void split_add(Arena &a, const float *W, int rows, int cols, int ld);
 int split_run(cudaStream_t st);

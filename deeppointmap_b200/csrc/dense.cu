@@ -481,7 +481,7 @@ extern "C" int dpm_linear_f32(const float *X, int ldx, const float *W, int ldw, 
 
 extern "C" size_t dpm_linear_workspace_bytes(int N, int K) {
     Arena a(nullptr, 0);
-    a.get<float>((size_t)2 * (N > 0 ? N : 0) * (K > 0 ? K : 0));
+    a.get<float>(split_floats(N > 0 ? N : 0, K > 0 ? K : 0));
     return a.off + 256;
 }
 
@@ -501,7 +501,7 @@ extern "C" int dpm_linear_ws_f32(const float *X, int ldx, const float *W, int ld
 
 extern "C" size_t dpm_linear_ln_workspace_bytes(int M, int N, int K) {
     Arena a(nullptr, 0);
-    a.get<float>((size_t)2 * (N > 0 ? N : 0) * (K > 0 ? K : 0));
+    a.get<float>(split_floats(N > 0 ? N : 0, K > 0 ? K : 0));
     a.get<float>((size_t)(M > 0 ? M : 0) * (N > 0 ? N : 0));
     return a.off + 256;
 }

@@ -143,30 +143,72 @@ __device__ __forceinline__ void produce_tile(const float *__restrict__ G, int ld
     }
 }
 
+// ---- cluster plumbing for the pre-split weight tiles --------------------------------------------------
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> this CTA's shared memory, completing `bytes` on the CTA's own mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// ... and into the same offsets of EVERY CTA of the cluster in `mask` (each one's mbarrier gets the bytes)
+__device__ __forceinline__ void bulk_g2s_multicast(unsigned dst, const void *src, unsigned bytes, unsigned bar,
+                                                   unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+// commit -> one arrival on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_multicast(unsigned bar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// W tile from the PRE-SPLIT copy of the weights (hi and lo as two compact (N, K) fp32 matrices, made
-// once per call by split_weights_kernel): asynchronous 16-byte copies straight into the swizzled
-// layout, no registers, no ALU; rows / K past the matrix are zero-filled (src-size 0).
-template <int ROWS>
-__device__ __forceinline__ void produce_tile_presplit(const float *__restrict__ Ghi, const float *__restrict__ Glo, int ld,
-                                                      int rows_total, int r0, int K, int k0, unsigned hi, unsigned lo,
-                                                      int tid) {
-    constexpr int ITER = ROWS * 8 / 128;
-#pragma unroll
-    for (int i = 0; i < ITER; ++i) {
-        const int idx = tid + i * 128, r = idx >> 3, c = idx & 7;
-        const int gr = r0 + r, gk = k0 + c * 4;
-        const bool ok = gr < rows_total && gk < K;
-        const size_t o = ok ? (size_t)gr * ld + gk : 0;
-        const unsigned off = swz(r, c);
-        cp_async16(hi + off, Ghi + o, ok ? 16u : 0u);
-        cp_async16(lo + off, Glo + o, ok ? 16u : 0u);
-    }
+// W tiles of PRE-SPLIT weights (split_weights_kernel, once per call): hi and lo are stored in global memory
+// K-block-major and already swizzled, [K block][row n][32 floats, 16-byte chunk c at (c ^ n) & 7], so the BN x 32 tile
+// of K block kb is ONE contiguous run of BN x 128 bytes that lands in the canonical SWIZZLE_128B layout by a plain 1-D
+// bulk copy (TMA engine, no registers, no ALU).  CTAs with consecutive row tiles form a CLUSTER along M: each one
+// fetches 1 / cluster of the tile's rows and MULTICASTS them into every CTA of the cluster, so a weight tile crosses
+// L2 -> SM once per cluster instead of once per CTA (the 64 MB of redundant weight reads of a 16 384 x 256 x 256
+// layer were what bounded its main loop: 12 us against 6.4 us of MMAs).
+#ifdef DPM_TC_PROFILE
+// developer build: wall-clock (globaltimer, ns) of the phases of every CTA of the last launch
+__device__ unsigned long long tc_prof[2048][6];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+#define TC_STAMP(i)                                                                                       \
+    do {                                                                                                  \
+        const int _c = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                    \
+        if (_c < 2048) tc_prof[_c][i] = gtimer();                                                         \
+    } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#endif
 
 struct LnArgs {  // fused LayerNorm epilogue: Y = act(LN_N(acc + bias + res) * gamma + beta + post)
     const float *gamma, *beta, *post;
@@ -195,10 +237,13 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
     const int nkb = (K + BK - 1) / BK;
     const unsigned full0 = s32(&bars[0]), empty0 = s32(&bars[STAGES]), accum = s32(&bars[2 * STAGES]);
 
+    const unsigned csize = PRESPLIT ? cluster_size() : 1u, crank = PRESPLIT ? cluster_rank() : 0u;
+    const unsigned short cmask = (unsigned short)((1u << csize) - 1u);
+    if (tid == 0) TC_STAMP(0);
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 128);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(full0 + 8 * s, PRESPLIT ? 129 : 128);  // X producers (+ the expect_tx arrival of the W copies)
+            mbar_init(empty0 + 8 * s, csize);                // the MMA warp of every CTA that receives this stage's W
         }
         mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,8 +256,10 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
     if (warp == 8) tmem_alloc(s32(&tmem_base_s), TCOLS);
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();  // nobody multicasts into a CTA whose mbarriers are not initialised yet
     tc_fence_after();
     const unsigned tmem_d = tmem_base_s;
+    if (tid == 0) TC_STAMP(1);
 
     if (warp < 8) {
         // ================= producers: group g takes the K blocks kb = g, g + 2, ... =================
@@ -221,12 +268,27 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
             const int s = kb % STAGES;
             mbar_wait(empty0 + 8 * s, (unsigned)(((kb / STAGES) & 1) ^ 1));
             unsigned char *st = smem + (size_t)s * STAGE_BYTES;
-            if (PRESPLIT)
-                produce_tile_presplit<BN>(W, W + wlo_off, ldw, N, n0, K, kb * BK, s32(st + 2 * A_TILE),
-                                          s32(st + 2 * A_TILE + B_TILE), ptid);
+            if (PRESPLIT) {
+                if (ptid == 0) {  // every CTA of the cluster has released this stage (empty barrier): send my rows
+                    const int rows = min(BN, N - n0);
+                    mbar_expect_tx(full0 + 8 * s, 2u * (unsigned)rows * 128u);
+                    const int per = (((rows + (int)csize - 1) / (int)csize) + 7) & ~7;
+                    const int r0 = (int)crank * per, nr = min(per, rows - r0);
+                    if (nr > 0) {
+                        const float *src = W + ((size_t)kb * N + n0 + r0) * BK;
+                        const unsigned dh = s32(st + 2 * A_TILE) + (unsigned)r0 * 128u, dl = dh + B_TILE;
+                        if (csize > 1) {
+                            bulk_g2s_multicast(dh, src, (unsigned)nr * 128u, full0 + 8 * s, cmask);
+                            bulk_g2s_multicast(dl, src + wlo_off, (unsigned)nr * 128u, full0 + 8 * s, cmask);
+                        } else {
+                            bulk_g2s(dh, src, (unsigned)nr * 128u, full0 + 8 * s);
+                            bulk_g2s(dl, src + wlo_off, (unsigned)nr * 128u, full0 + 8 * s);
+                        }
+                    }
+                }
+            }
             produce_tile<BM>(X, ldx, M, m0, K, kb * BK, st, st + A_TILE, ptid);
-            if (PRESPLIT) cp_async_wait_all();
-            else produce_tile<BN>(W, ldw, N, n0, K, kb * BK, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ptid);
+            if (!PRESPLIT) produce_tile<BN>(W, ldw, N, n0, K, kb * BK, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ptid);
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(full0 + 8 * s);
         }
@@ -237,6 +299,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
         // meets the residual as whole 128-byte row segments, 4 rows per warp instruction.
         mbar_wait(accum, 0u);
         tc_fence_after();
+        if (tid == 0) TC_STAMP(3);
         const int quarter = warp & 3;  // the TMEM lane quarter this warp may read
         constexpr int CHALF = BN >= 64 ? BN / 2 : BN;  // columns per producer group in the epilogue
         constexpr int TLD = 36;                        // staging row stride (floats): 16-byte aligned, conflict-free
@@ -407,6 +470,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
             const int s = kb % STAGES;
             mbar_wait(full0 + 8 * s, (unsigned)((kb / STAGES) & 1));
             tc_fence_after();
+            if (kb == 0) TC_STAMP(2);
             const unsigned sa = s32(smem + (size_t)s * STAGE_BYTES);
             const unsigned long long ah = smem_desc(sa), al = smem_desc(sa + A_TILE);
             const unsigned long long bh = smem_desc(sa + 2 * A_TILE), bl = smem_desc(sa + 2 * A_TILE + B_TILE);
@@ -417,16 +481,21 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
                 mma_tf32(tmem_d + BN, ah + ko, bl + ko, IDESC, (kb | j) != 0 ? 1u : 0u);
                 mma_tf32(tmem_d + BN, al + ko, bh + ko, IDESC, 1u);
             }
-            mma_commit(empty0 + 8 * s);  // stage free once these MMAs have read it
+            // stage free once these MMAs have read it -- for every CTA that multicasts into it
+            if (csize > 1) mma_commit_multicast(empty0 + 8 * s, cmask);
+            else mma_commit(empty0 + 8 * s);
         }
         mma_commit(accum);
     }
+    if (tid == 0) TC_STAMP(4);
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();  // no CTA leaves while a peer's commits / copies can still target it
     if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_d, TCOLS);
     }
+    if (tid == 0) TC_STAMP(5);
 }
 
 template <int BN, int STAGES, bool PRESPLIT, bool LN = false>
@@ -441,9 +510,35 @@ static int launch_t(const float *X, int ldx, long long sX, const float *W, int l
         DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured |= devbit;
     }
-    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch);
-    kern<<<grid, THREADS, smem, st>>>(X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY, wlo_off, ln);
-    DPM_CHECK_LAUNCH(LN ? "linear_ln_tc" : "linear_tc", st);
+    const int mt = (M + BM - 1) / BM;
+    // pre-split weights: clusters of row tiles share every weight tile by multicast (the grid is padded to whole
+    // clusters; a CTA past the last row tile loads zeros, stores nothing and keeps the cluster's pipeline in step)
+    static const int cl_env = getenv("DPM_TC_CLUSTER") ? atoi(getenv("DPM_TC_CLUSTER")) : 0;
+    int cl = 1;
+    if (PRESPLIT) {
+        // measured (round 2, 32-frame steps on 5 streams): cluster 1 -> 6613 frames/s, 2 -> 6474, 4 -> 6304.  The weight
+        // re-reads were NOT what bounds the main loop (it runs at 76 % of the tf32 MMA peak either way); clusters only
+        // add co-scheduling constraints and two cluster barriers.  So the default is one CTA per "cluster" (plain bulk
+        // copies); DPM_TC_CLUSTER=2|4 keeps the multicast path measurable.
+        cl = cl_env > 0 ? cl_env : 1;
+        if (cl != 1 && cl != 2 && cl != 4 && cl != 8) cl = 1;
+        if (cl > mt) cl = 1;
+    }
+    dim3 grid((mt + cl - 1) / cl * cl, (N + BN - 1) / BN, nbatch);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    DPM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, X, ldx, W, ldw, bias, res, ldres, Y, ldy, M, N, K, act, sX, sW, sY, wlo_off, ln));
+    count_launch(LN ? "linear_ln_tc" : "linear_tc", st);
     return DPM_OK;
 }
 
@@ -466,7 +561,7 @@ bool linear_ln_tc_launch(const float *X, int ldx, const float *W, int ldw, const
     if (!Ws || getenv("DPM_NO_TC")) return false;
     prof_note((long long)M, (long long)N * K);
     const tc::LnArgs ln{gamma, beta, post, ldpost};
-    const long long lo = (long long)N * K;
+    const long long lo = (long long)N * ((K + 31) & ~31);
 #define DPM_TC_ARGS X, ldx, 0, Ws, K, 0, bias, res, ldres, Y, ldy, 0, M, N, K, 1, act, lo, st, ln
     if (N <= 32) *rc = tc::launch_t<32, 4, true, true>(DPM_TC_ARGS);
     else if (N <= 64) *rc = tc::launch_t<64, 4, true, true>(DPM_TC_ARGS);
@@ -493,7 +588,7 @@ int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int 
     // pre-split weights registered for this call (split_weights_*): hi at the returned pointer, lo right after
     const float *Ws = (nbatch == 1) ? split_lookup(W, N, K, ldw) : nullptr;
     if (Ws) {
-        const long long lo = (long long)N * K;
+        const long long lo = (long long)N * ((K + 31) & ~31);
 #define DPM_TC_ARGS X, ldx, sX, Ws, K, 0, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, lo, st
         if (N <= 32) return tc::launch_t<32, 4, true>(DPM_TC_ARGS);
         if (N <= 64) return tc::launch_t<64, 4, true>(DPM_TC_ARGS);
@@ -526,32 +621,38 @@ struct SplitTable {
 static thread_local SplitTable g_split;
 static thread_local int g_nsplit = 0;
 
+// dst: hi then lo, each (K blocks of 32) x rows x 32 floats, chunk c of row n stored at chunk (c ^ n) & 7; K padded
+// to a multiple of 32 with zeros
 __global__ void __launch_bounds__(256) split_weights_kernel(const __grid_constant__ SplitTable t) {
     const SplitJob j = t.job[blockIdx.y];
-    const int n = j.rows * j.cols;
+    const int kpad = j.pad, n = j.rows * kpad;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const int r = i / j.cols, c = i - r * j.cols;
-        const float v = j.src[(size_t)r * j.ld + c];
+        const int r = i / kpad, c = i - r * kpad;
+        const float v = c < j.cols ? j.src[(size_t)r * j.ld + c] : 0.f;
         const float h = tc::tf32_rna(v);
-        j.dst[i] = h;
-        j.dst[(size_t)n + i] = tc::tf32_rna(v - h);
+        const int kb = c >> 5, ch = (c >> 2) & 7, e = c & 3;
+        const size_t o = ((size_t)kb * j.rows + r) * 32 + (((ch ^ r) & 7) << 2) + e;
+        j.dst[o] = h;
+        j.dst[(size_t)n + o] = tc::tf32_rna(v - h);
     }
 }
+
+size_t split_floats(int rows, int cols) { return (size_t)2 * rows * ((cols + 31) & ~31); }
 
 void split_begin() { g_nsplit = 0; }
 
 void split_add(Arena &a, const float *W, int rows, int cols, int ld) {
     if (rows < 8 || cols < 4 || (cols & 3)) return;  // never taken by the tensor-core path
-    float *dst = a.get<float>((size_t)2 * rows * cols);
+    float *dst = a.get<float>(split_floats(rows, cols));
     if (a.dry || !dst || !W || g_nsplit >= SPLIT_MAX) return;
     SplitJob &j = g_split.job[g_nsplit++];
-    j.src = W; j.dst = dst; j.rows = rows; j.cols = cols; j.ld = ld; j.pad = 0;
+    j.src = W; j.dst = dst; j.rows = rows; j.cols = cols; j.ld = ld; j.pad = (cols + 31) & ~31;
 }
 
 int split_run(cudaStream_t st) {
     if (g_nsplit == 0) return DPM_OK;
     int maxn = 0;
-    for (int i = 0; i < g_nsplit; ++i) maxn = g_split.job[i].rows * g_split.job[i].cols > maxn ? g_split.job[i].rows * g_split.job[i].cols : maxn;
+    for (int i = 0; i < g_nsplit; ++i) maxn = g_split.job[i].rows * g_split.job[i].pad > maxn ? g_split.job[i].rows * g_split.job[i].pad : maxn;
     int gx = (maxn + 1023) / 1024;  // ~4 elements per thread for the largest matrix
     gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
     split_weights_kernel<<<dim3(gx, g_nsplit, 1), 256, 0, st>>>(g_split);
@@ -568,3 +669,10 @@ const float *split_lookup(const float *W, int rows, int cols, int ld) {
 }
 
 }  // namespace dpm
+
+#ifdef DPM_TC_PROFILE
+extern "C" int dpm_debug_tc_profile(unsigned long long *out, int nctas) {
+    if (cudaMemcpyFromSymbol(out, dpm::tc::tc_prof, sizeof(unsigned long long) * 6 * (nctas > 2048 ? 2048 : nctas)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
