@@ -135,8 +135,35 @@ class _Missing:
                                   "(pose-graph optimisation: run with enable_global_optimization: false)")
 
 
+class _Registration:
+    """only what inference WITHOUT loop closure touches; the pose-graph optimiser raises"""
+
+    @staticmethod
+    def get_information_matrix_from_point_clouds(source, target, max_correspondence_distance, transformation):
+        """open3d pipelines/registration/Registration.cpp GetInformationMatrixFromPointClouds: for every source point
+        whose transformed position has a target point within the distance, that target point (x, y, z) adds G^T G of
+        G = [[0, z, -y, 1, 0, 0], [-z, 0, x, 0, 1, 0], [y, -x, 0, 0, 0, 1]] -- the formula the reference restates for
+        its pytorch3d branch (system/modules/utils.py:70-101)."""
+        from scipy.spatial import cKDTree
+        T = np.asarray(transformation, dtype=np.float64).reshape(4, 4)
+        src = np.asarray(source.points, dtype=np.float64).reshape(-1, 3) @ T[:3, :3].T + T[:3, 3]
+        tgt = np.asarray(target.points, dtype=np.float64).reshape(-1, 3)
+        d, idx = cKDTree(tgt).query(src, k=1, distance_upper_bound=float(max_correspondence_distance))
+        t = tgt[idx[np.isfinite(d)]]
+        x, y, z = t[:, 0], t[:, 1], t[:, 2]
+        o, l = np.zeros_like(x), np.ones_like(x)
+        GTG = np.zeros((6, 6))
+        for row in (np.stack([o, z, -y, l, o, o], 1), np.stack([-z, o, x, o, l, o], 1), np.stack([y, -x, o, o, o, l], 1)):
+            GTG += row.T @ row
+        return GTG
+
+    def __getattr__(self, name):
+        raise NotImplementedError(f"open3d shim: open3d.pipelines.registration.{name} needs the real open3d package "
+                                  "(pose-graph optimisation: run with enable_global_optimization: false)")
+
+
 class _Pipelines:
-    registration = _Missing("pipelines.registration")
+    registration = _Registration()
 
 
 pipelines = _Pipelines()

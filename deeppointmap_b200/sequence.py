@@ -56,21 +56,32 @@ def trajectory(n_frames: int, step_m: float = 1.0, max_yaw_deg: float = 2.0) -> 
 
 @torch.no_grad()
 def corridor_frames(world: torch.Tensor, poses: torch.Tensor, n_points: int, seed: int = 0, max_range_m: float = 60.0,
-                    jitter_m: float = 0.01, scale: float = 60.0) -> torch.Tensor:
+                    jitter_m: float = 0.01, scale: float = 60.0, stable: bool = False) -> torch.Tensor:
     """What the sensor sees: (F, 3, n_points) fp32 normalised clouds in the sensor frames (1 m <= |p| <= range,
-    a fresh random subset and jitter per frame) on the world tensor's device."""
+    a fresh random subset and jitter per frame) on the world tensor's device.  stable=True: every world point has a
+    fixed priority and a frame keeps the n_points in range with the highest one, so consecutive frames sample the
+    SAME surface points (a static world re-observed, as in bench.py's pairs) instead of fresh ones."""
     dev = world.device
     g = torch.Generator(device=dev).manual_seed(int(seed))
     out = torch.empty((poses.shape[0], 3, n_points), dtype=torch.float32, device=dev)
+    prio = None
+    if stable:
+        gp = torch.Generator(device=dev).manual_seed(977)
+        prio = torch.rand(world.shape[1], generator=gp, device=dev)
     for i in range(poses.shape[0]):
         Tinv = torch.linalg.inv(poses[i]).to(device=dev, dtype=torch.float32)
         near = ((world[0] - float(poses[i, 0, 3])).abs() <= max_range_m)
         p = Tinv[:3, :3] @ world[:, near] + Tinv[:3, 3:]
         d = p.norm(dim=0)
-        p = p[:, (d >= 1.0) & (d <= max_range_m)]
+        inr = (d >= 1.0) & (d <= max_range_m)
+        p = p[:, inr]
         if p.shape[1] < n_points:
             raise ValueError(f"frame {i}: only {p.shape[1]} world points in range, need {n_points} (raise ground_density)")
-        sel = torch.randperm(p.shape[1], generator=g, device=dev)[:n_points]
+        if stable:
+            sel = torch.topk(prio[near][inr], n_points).indices
+            sel = sel[torch.randperm(n_points, generator=g, device=dev)]
+        else:
+            sel = torch.randperm(p.shape[1], generator=g, device=dev)[:n_points]
         out[i] = (p[:, sel] + jitter_m * torch.randn((3, n_points), generator=g, device=dev)) / scale
     return out
 

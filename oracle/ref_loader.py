@@ -43,10 +43,28 @@ def vendor() -> str:
                     dst = os.path.join(VENDORED, rel, f)
                     if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(os.path.join(base, f)):
                         shutil.copyfile(os.path.join(base, f), dst)
+    sample = os.path.join(SRC, "data", "sample")   # the 11 real KITTI scans the reference ships: the pipeline test's input
+    for base, _, files in os.walk(sample):
+        rel = os.path.relpath(base, SRC)
+        for f in files:
+            if f.endswith(".bin"):
+                os.makedirs(os.path.join(VENDORED, rel), exist_ok=True)
+                dst = os.path.join(VENDORED, rel, f)
+                if not os.path.exists(dst):
+                    shutil.copyfile(os.path.join(base, f), dst)
     ck, dst = os.path.join(SRC, "DeepPointMapAAAI.pth"), os.path.join(ROOT, "oracle", "_ref", "DeepPointMapAAAI.pth")
     if os.path.exists(ck) and not os.path.exists(dst):
         shutil.copyfile(ck, dst)
     return VENDORED
+
+
+def sample_frames():
+    """sorted paths of the real KITTI scans shipped with the reference (data/sample/seq06/velodyne/*.bin)"""
+    root = ref_root()
+    d = os.path.join(root, "data", "sample", "seq06", "velodyne") if root else ""
+    if not os.path.isdir(d):
+        return []
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".bin"))
 
 
 def checkpoint_path():
