@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-batch1", action="store_true")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the extra legs (sustained run, strong scaling, caller sizes, uniform cube, reference on the GPU)")
+    ap.add_argument("--pipeline-frames", type=int, default=200, help="synthetic scans of the pipeline/infer.py leg (0 = skip)")
     ap.add_argument("--sustain-s", type=float, default=1.5, help="minimum device time of the sustained leg")
     ap.add_argument("--strong-frames", type=int, default=32, help="GLOBAL frames of the strong-scaling leg (BASELINE configs[3])")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (0 = auto)")
@@ -416,6 +417,53 @@ def reference_gpu_leg(cfg, dev, n, pts2):
     ms = e0.elapsed_time(e1) / reps
     return {"frames_per_s": 1e3 / ms, "ms_per_frame": ms, "what": kind, "frames_timed": reps}
 
+def pipeline_leg(n_synth, n_points, dev):
+    """BASELINE configs[4]: the reference's own pipeline/infer.py, unmodified, on the drop-in modules -- over
+    `n_synth` synthetic KITTI-shape .bin scans (SURVEY 8d's config-5 generator) and over the reference's real sample
+    scans (51 frames forth and back) when they travelled.  frames/s from the reference's own per-stage timers
+    (ResultLogger.log_time) and as whole-process wall clock (interpreter start, checkpoint load, file IO included)."""
+    import shutil
+    import tempfile
+    from oracle import ref_loader
+    from deeppointmap_b200 import pipeline
+    ref, weight = ref_loader.ref_root(), ref_loader.checkpoint_path()
+    if ref is None or weight is None:
+        return {"unavailable": "reference sources not on this box (oracle/_ref/reference is made by build())"}
+    work = tempfile.mkdtemp(prefix="dpm_pipeline_")
+    out = {}
+    try:
+        jobs = []
+        if n_synth > 0:
+            seq = os.path.join(work, "synth", "0")
+            pipeline.write_synthetic_sequence(seq, n_synth, n_points, seed=5, device=dev)
+            jobs.append(("synthetic", seq, n_synth, {"edge_confidence_drop": 0.0, "edge_rmse_drop": 1e9}))
+        real = ref_loader.sample_frames()
+        if len(real) >= 2:
+            seq = os.path.join(work, "real", "0")
+            pipeline.write_boomerang_sequence(seq, real, 51)
+            jobs.append(("real_kitti_sample", seq, 51, None))
+        for name, seq, nf, over in jobs:
+            y = pipeline.write_yaml(os.path.join(work, f"{name}.yaml"), ref, [seq], os.path.join(work, f"out_{name}"),
+                                    transforms=pipeline.DEFAULT_TRANSFORMS, slam_overrides=over)
+            r = pipeline.run_infer_subprocess(ref, "b200", y, weight, timeout=600)
+            rec = {"frames": nf, "returncode": r["returncode"], "wall_s": r["wall_s"], "wall_frames_per_s": nf / r["wall_s"],
+                   "loop_frames_per_s": r["loop_frames_per_s"], "stage_mean_s": r["stage_mean_s"],
+                   "transforms": list(pipeline.DEFAULT_TRANSFORMS)}
+            if r["returncode"] != 0:
+                rec["stderr_tail"] = r["stderr_tail"][-300:]
+            try:
+                rec["scans_in_trajectory"] = int(len(pipeline.load_trajectory(os.path.join(work, f"out_{name}"))[0]))
+            except Exception:  # noqa: BLE001
+                rec["scans_in_trajectory"] = None
+            out[name] = rec
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    out["what"] = ("python -m deeppointmap_b200.pipeline --impl b200 -> <reference>/pipeline/infer.py unmodified (single-thread "
+                   "mode: SlamSystem.step per scan, batch 1, loop closure off); see tests/test_gpu_pipeline.py for the "
+                   "trajectory comparison against the reference's own modules")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------------------------
@@ -686,7 +734,7 @@ def main():
                 batch1["cuda_graph_error"] = str(e)[:200]
 
         # ---- the other caller shapes, the adversarial cloud, the reference on this GPU (rank 0 of a 1-GPU run) ----
-        callers = cube = ref_gpu = None
+        callers = cube = ref_gpu = pipe = None
         if not args.no_extra and world == 1:
             tpk, _ = tensor_peak()
             try:
@@ -701,6 +749,10 @@ def main():
                 ref_gpu = reference_gpu_leg(cfg, dev, n, dev_pool[0][:5])
             except Exception as e:  # noqa: BLE001
                 ref_gpu = {"error": repr(e)[:300]}
+            try:
+                pipe = pipeline_leg(args.pipeline_frames, n, dev)
+            except Exception as e:  # noqa: BLE001
+                pipe = {"error": repr(e)[:300]}
 
         # ---- per-kernel profile passes (a CUDA event after every launch, on the launching stream) ---------
         # "isolated": the step alone on one stream.  "concurrent": the profiled step on stream 0 while the other
@@ -849,7 +901,7 @@ def main():
         "kernel_totals_concurrent_ms_per_step": kern_totals_conc,
         "profiled_step_ms": prof_total, "wall_ms_per_step": 1e3 * t_wall / K,
         "sustained": sustained, "strong": strong, "caller_sizes": callers, "index_ops_by_cloud": cube,
-        "reference_gpu": ref_gpu,
+        "reference_gpu": ref_gpu, "pipeline_infer": pipe,
         "vs_reference_gpu": (value / ref_gpu["frames_per_s"]) if (ref_gpu and ref_gpu.get("frames_per_s") and world == 1) else None,
     }
 

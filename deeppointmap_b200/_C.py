@@ -65,10 +65,11 @@ _SIGS = {
     "dpm_encoder_workspace_bytes": ([ctypes.POINTER(EncoderDesc), _i, _i], _sz),
     "dpm_encoder_num_weights": ([ctypes.POINTER(EncoderDesc)], _i),
     "dpm_encoder_out_points": ([ctypes.POINTER(EncoderDesc)], _i),
-    "dpm_registration_forward": ([ctypes.POINTER(DecoderDesc), _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz,
-                                  _vp], _i),
+    "dpm_registration_forward": ([ctypes.POINTER(DecoderDesc), _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
+                                  _sz, _vp], _i),
     "dpm_registration_workspace_bytes": ([ctypes.POINTER(DecoderDesc), _i, _i, _i, _i], _sz),
-    "dpm_loop_detection_forward": ([ctypes.POINTER(DecoderDesc), _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp], _i),
+    "dpm_loop_detection_forward": ([ctypes.POINTER(DecoderDesc), _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz,
+                                    _vp], _i),
     "dpm_loop_detection_workspace_bytes": ([ctypes.POINTER(DecoderDesc), _i, _i, _i], _sz),
     "dpm_decoder_num_weights": ([ctypes.POINTER(DecoderDesc)], _i),
     "dpm_posenc_f32": ([_vp, _i, _vp, _i, _vp, _i, _i, _vp], _i),

@@ -16,7 +16,8 @@ namespace dpm {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dec_unpack_kernel(const float *__restrict__ src, const float *__restrict__ dst, int M, int N, int Cf,
-                  float *__restrict__ fea, float4 *__restrict__ xyz) {
+                  float *__restrict__ fea, float4 *__restrict__ xyz, const uint8_t *__restrict__ src_pad,
+                  const uint8_t *__restrict__ dst_pad, uint8_t *__restrict__ rowmask) {
     __shared__ float tile[32][33];
     const int z = blockIdx.z, p = z >> 1, side = z & 1;
     const int L = side ? N : M;
@@ -36,8 +37,13 @@ dec_unpack_kernel(const float *__restrict__ src, const float *__restrict__ dst, 
     }
     if (blockIdx.y == 0 && ty == 0) {
         const int l = l0 + tx;
-        if (l < L)
+        if (l < L) {
             xyz[row0 + l] = make_float4(in[(size_t)Cf * L + l], in[(size_t)(Cf + 1) * L + l], in[(size_t)(Cf + 2) * L + l], 0.f);
+            if (rowmask) {
+                const uint8_t *pm = side ? dst_pad : src_pad;
+                rowmask[row0 + l] = pm ? (pm[(size_t)p * L + l] != 0) : 0;
+            }
+        }
     }
 }
 
@@ -97,8 +103,9 @@ template <bool LONG>
 __global__ void __launch_bounds__(AT_T, LONG ? 1 : 512 / AT_T)
 attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__ Kp, int ldk,
                     const float *__restrict__ Vp, int ldv, float *__restrict__ O, int ldo, const int *__restrict__ prob,
-                    int M, int N, int mode) {
+                    int M, int N, int mode, const uint8_t *__restrict__ kmask) {
     __shared__ __align__(16) unsigned Kh[AT_BK * AT_LD], Kl[AT_BK * AT_LD], Vh[AT_BK * AT_LD], Vl[AT_BK * AT_LD];
+    __shared__ uint8_t kdrop[AT_BK];  // key_padding_mask of the staged keys (descriptor_attention.py:33-42): 1 = ignored
     const int z = blockIdx.z, head = blockIdx.y;
     int q0, Lq, k0, Lk;
     if (prob) {
@@ -163,6 +170,7 @@ attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restric
             h.w = tf32_bits(vv.w); l.w = tf32_bits(vv.w - __uint_as_float(h.w));
             *reinterpret_cast<uint4 *>(&Vh[key * AT_LD + 4 * part]) = h;
             *reinterpret_cast<uint4 *>(&Vl[key * AT_LD + 4 * part]) = l;
+            if (kmask && part == 0) kdrop[key] = (c0 + key < Lk) ? kmask[k0 + c0 + key] : 1;
         }
         __syncthreads();
 
@@ -178,6 +186,13 @@ attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restric
                 mma_tf32_16n8k8(sc[j], ql[s], b0h, b1h);
                 mma_tf32_16n8k8(sc[j], qh[s], b0l, b1l);
                 mma_tf32_16n8k8(sc[j], qh[s], b0h, b1h);
+            }
+        }
+        if (kmask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (kdrop[8 * j + 2 * t]) { sc[j][0] = NEG; sc[j][2] = NEG; }
+                if (kdrop[8 * j + 2 * t + 1]) { sc[j][1] = NEG; sc[j][3] = NEG; }
             }
         }
         const int nvalid = Lk - c0;
@@ -199,7 +214,11 @@ attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restric
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        if (kmask) {  // every key so far masked: keep the exponents finite (the tile then contributes exp(-inf) = 0)
+            mn0 = mn0 == NEG ? 0.f : mn0;
+            mn1 = mn1 == NEG ? 0.f : mn1;
+        }
         const float corr0 = expf(m0 - mn0), corr1 = expf(m1 - mn1);
         m0 = mn0; m1 = mn1;
         l0 *= corr0; l1 *= corr1;
@@ -270,15 +289,16 @@ attention_tc_kernel(const float *__restrict__ Q, int ldq, const float *__restric
 }
 
 int attention_launch(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out, int ldo,
-                     const int *prob, int nprob, int maxLq, int M, int N, int mode, int heads, cudaStream_t st) {
+                     const int *prob, int nprob, int maxLq, int M, int N, int mode, int heads, cudaStream_t st,
+                     const uint8_t *kmask = nullptr) {
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
     if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
     dim3 grid((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
     // the longest key range of the launch decides (prob == nullptr: the two sides of the pairs; else the caller's table,
     // which this host code cannot read: the accurate variant then)
     const bool lng = prob ? true : (M > 512 || N > 512);
-    if (lng) attention_tc_kernel<true><<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
-    else attention_tc_kernel<false><<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode);
+    if (lng) attention_tc_kernel<true><<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode, kmask);
+    else attention_tc_kernel<false><<<grid, AT_T, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, prob, M, N, mode, kmask);
     DPM_CHECK_LAUNCH("attention", st);
     return DPM_OK;
 }
@@ -680,8 +700,9 @@ static int dec_split(const dpm_decoder_desc *d, const DecW *w, bool registration
 }
 
 // _descriptor_attention_forward (decoder.py:145-162): -> F (R, C) correlated features, xyz (R)
-static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float *src, const float *dst, int P, int M,
-                           int N, Arena &a, float **F_out, float4 **xyz_out, cudaStream_t st) {
+static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float *src, const float *dst,
+                           const uint8_t *src_pad, const uint8_t *dst_pad, int P, int M, int N, Arena &a, float **F_out,
+                           float4 **xyz_out, cudaStream_t st) {
     const bool dry = a.dry;
     const int C = d->model_channel, Cf = d->in_channel, H = d->heads;
     const int R = P * (M + N);
@@ -694,14 +715,16 @@ static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float
     float *y = a.get<float>((size_t)R * C);
     float *qkv = a.get<float>((size_t)R * 3 * C);
     float *att = a.get<float>((size_t)R * C);
+    uint8_t *rowmask = a.get<uint8_t>((size_t)R);  // key_padding_mask per token row (only read when a mask was given)
     if (!a.ok()) return fail(DPM_ERR_WORKSPACE, "decoder: workspace too small");
+    const uint8_t *km = (src_pad || dst_pad) ? rowmask : nullptr;
     *F_out = x;
     *xyz_out = xyz;
     if (dry) return DPM_OK;
     const int npf = C / 3 / 2 * 2;
     const int maxL = M > N ? M : N;
     dim3 g((maxL + 31) / 32, (Cf + 31) / 32, 2 * P);
-    dec_unpack_kernel<<<g, 256, 0, st>>>(src, dst, M, N, Cf, fea, xyz);
+    dec_unpack_kernel<<<g, 256, 0, st>>>(src, dst, M, N, Cf, fea, xyz, src_pad, dst_pad, km ? rowmask : nullptr);
     DPM_CHECK_LAUNCH("dec_unpack", st);
     DPM_TRY(posenc_launch(reinterpret_cast<const float *>(xyz), 4, w.dim_t, npf, pos, R, C, st));
     // x = projection(fea) + pos   (the "+ pos" of the first layer, descriptor_attention.py:31)
@@ -711,11 +734,11 @@ static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float
         const bool last = l == d->attention_layers - 1;
         // self attention (shared weights for src and dst), add & norm1, then "+ pos" again
         DPM_TRY(linear_launch(x, C, L.sa_in_w, C, L.sa_in_b, nullptr, 0, qkv, 3 * C, R, 3 * C, C, DPM_ACT_NONE, st));
-        DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 0, H, st));
+        DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 0, H, st, km));
         DPM_TRY(linear_ln_launch(att, C, L.sa_out_w, C, L.sa_out_b, x, C, L.n1_w, L.n1_b, pos, C, y, x, C, R, C, C, DPM_ACT_NONE, st));
         // cross attention both ways, add & norm2
         DPM_TRY(linear_launch(x, C, L.ca_in_w, C, L.ca_in_b, nullptr, 0, qkv, 3 * C, R, 3 * C, C, DPM_ACT_NONE, st));
-        DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 1, H, st));
+        DPM_TRY(attention_launch(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, nullptr, 2 * P, maxL, M, N, 1, H, st, km));
         DPM_TRY(linear_ln_launch(att, C, L.ca_out_w, C, L.ca_out_b, x, C, L.n2_w, L.n2_b, nullptr, 0, y, x, C, R, C, C, DPM_ACT_NONE, st));
         // mlp, add & norm3 (+ pos for the next layer)
         DPM_TRY(linear_launch(x, C, L.m0_w, C, L.m0_b, nullptr, 0, att, C, R, C, C, DPM_ACT_RELU, st));
@@ -726,8 +749,8 @@ static int attention_stack(const dpm_decoder_desc *d, const DecW &w, const float
 }
 
 static int registration_run(const dpm_decoder_desc *d, const float *const *weights, const float *src,
-                            const float *dst, int P, int M, int N, int k, float *result, float *conf_out, Arena &a,
-                            cudaStream_t st) {
+                            const float *dst, const uint8_t *src_pad, const uint8_t *dst_pad, int P, int M, int N, int k,
+                            float *result, float *conf_out, Arena &a, cudaStream_t st) {
     const bool dry = a.dry;
     if (P <= 0 || M <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "registration: bad shape P=%d M=%d N=%d", P, M, N);
     if (k <= 0 || (long long)k > (long long)M * N) return fail(DPM_ERR_SHAPE, "registration: k=%d pairs out of range", k);
@@ -739,7 +762,7 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     float4 *xyz = nullptr;
     if (d->attention_layers < 0 || d->attention_layers > 16) return fail(DPM_ERR_SHAPE, "decoder: attention_layers");
     DPM_TRY(dec_split(d, dry ? nullptr : &w, true, a, st));
-    DPM_TRY(attention_stack(d, w, src, dst, P, M, N, a, &F, &xyz, st));
+    DPM_TRY(attention_stack(d, w, src, dst, src_pad, dst_pad, P, M, N, a, &F, &xyz, st));
     float *h = a.get<float>((size_t)R * C);
     float *sim = a.get<float>((size_t)R * C);
     float *S = a.get<float>((size_t)P * M * N);
@@ -786,8 +809,9 @@ static int registration_run(const dpm_decoder_desc *d, const float *const *weigh
     return DPM_OK;
 }
 
-static int loop_run(const dpm_decoder_desc *d, const float *const *weights, const float *src, const float *dst, int P,
-                    int M, int N, float *prob, Arena &a, cudaStream_t st) {
+static int loop_run(const dpm_decoder_desc *d, const float *const *weights, const float *src, const float *dst,
+                    const uint8_t *src_pad, const uint8_t *dst_pad, int P, int M, int N, float *prob, Arena &a,
+                    cudaStream_t st) {
     const bool dry = a.dry;
     if (P <= 0 || M <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "loop_detection: bad shape");
     DecW w;
@@ -797,7 +821,7 @@ static int loop_run(const dpm_decoder_desc *d, const float *const *weights, cons
     float4 *xyz = nullptr;
     if (d->attention_layers < 0 || d->attention_layers > 16) return fail(DPM_ERR_SHAPE, "decoder: attention_layers");
     DPM_TRY(dec_split(d, dry ? nullptr : &w, false, a, st));
-    DPM_TRY(attention_stack(d, w, src, dst, P, M, N, a, &F, &xyz, st));
+    DPM_TRY(attention_stack(d, w, src, dst, src_pad, dst_pad, P, M, N, a, &F, &xyz, st));
     float *h = a.get<float>((size_t)R * C);
     float *g = a.get<float>((size_t)R * C);
     float *mean = a.get<float>((size_t)P * 2 * C);
@@ -827,38 +851,40 @@ extern "C" int dpm_decoder_num_weights(const dpm_decoder_desc *desc) { return de
 extern "C" size_t dpm_registration_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N, int k) {
     if (!desc) return 0;
     Arena a(nullptr, 0);
-    if (registration_run(desc, nullptr, nullptr, nullptr, P, M, N, k, nullptr, nullptr, a, nullptr) != DPM_OK) return 0;
+    if (registration_run(desc, nullptr, nullptr, nullptr, nullptr, nullptr, P, M, N, k, nullptr, nullptr, a, nullptr) != DPM_OK) return 0;
     // loop detection shares the attention stack; its extra buffers are smaller than registration's
     return a.off + 256;
 }
 
 extern "C" int dpm_registration_forward(const dpm_decoder_desc *desc, const float *const *weights, int n_weights,
-                                        const float *src, const float *dst, int P, int M, int N, int k, float *result,
+                                        const float *src, const float *dst, const uint8_t *src_pad,
+                                        const uint8_t *dst_pad, int P, int M, int N, int k, float *result,
                                         float *conf_out, void *ws, size_t ws_bytes, dpm_stream_t stream) {
     if (!desc || !weights || !src || !dst || !result || !conf_out || !ws) return fail(DPM_ERR_ARG, "registration: null pointer");
     if (n_weights != dec_num_weights(desc) + 1)
         return fail(DPM_ERR_SHAPE, "registration: got %d weight tensors, expected %d", n_weights, dec_num_weights(desc) + 1);
     prof_mark((cudaStream_t)stream);
     Arena a(ws, ws_bytes);
-    return registration_run(desc, weights, src, dst, P, M, N, k, result, conf_out, a, (cudaStream_t)stream);
+    return registration_run(desc, weights, src, dst, src_pad, dst_pad, P, M, N, k, result, conf_out, a, (cudaStream_t)stream);
 }
 
 extern "C" size_t dpm_loop_detection_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N) {
     if (!desc) return 0;
     Arena a(nullptr, 0);
-    if (loop_run(desc, nullptr, nullptr, nullptr, P, M, N, nullptr, a, nullptr) != DPM_OK) return 0;
+    if (loop_run(desc, nullptr, nullptr, nullptr, nullptr, nullptr, P, M, N, nullptr, a, nullptr) != DPM_OK) return 0;
     return a.off + 256;
 }
 
 extern "C" int dpm_loop_detection_forward(const dpm_decoder_desc *desc, const float *const *weights, int n_weights,
-                                          const float *src, const float *dst, int P, int M, int N, float *prob,
-                                          void *ws, size_t ws_bytes, dpm_stream_t stream) {
+                                          const float *src, const float *dst, const uint8_t *src_pad,
+                                          const uint8_t *dst_pad, int P, int M, int N, float *prob, void *ws,
+                                          size_t ws_bytes, dpm_stream_t stream) {
     if (!desc || !weights || !src || !dst || !prob || !ws) return fail(DPM_ERR_ARG, "loop_detection: null pointer");
     if (n_weights != dec_num_weights(desc) + 1)
         return fail(DPM_ERR_SHAPE, "loop_detection: got %d weight tensors, expected %d", n_weights, dec_num_weights(desc) + 1);
     prof_mark((cudaStream_t)stream);
     Arena a(ws, ws_bytes);
-    return loop_run(desc, weights, src, dst, P, M, N, prob, a, (cudaStream_t)stream);
+    return loop_run(desc, weights, src, dst, src_pad, dst_pad, P, M, N, prob, a, (cudaStream_t)stream);
 }
 
 extern "C" int dpm_posenc_f32(const float *xyz, int ldx, const float *dim_t, int npf, float *emb, int R, int C,

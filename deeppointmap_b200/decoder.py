@@ -154,14 +154,27 @@ class Decoder(nn.Module):
     def _prep(x: Tensor) -> Tensor:
         return x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous()
 
+    @staticmethod
+    def _mask(mask: Optional[Tensor], P: int, L: int, dev) -> Optional[Tensor]:
+        """key-padding mask (P, L), True = padded -> contiguous uint8 on the device, or None"""
+        if mask is None:
+            return None
+        if mask.dim() == 1:
+            mask = mask.unsqueeze(0)
+        if tuple(mask.shape) != (P, L):
+            raise ValueError(f"padding mask must be ({P}, {L}), got {tuple(mask.shape)}")
+        return mask.to(device=dev, dtype=torch.bool).to(torch.uint8).contiguous()
+
     @torch.no_grad()
-    def registration_forward_batch(self, src: Tensor, dst: Tensor, num_sample: Union[int, float] = 0.5):
+    def registration_forward_batch(self, src: Tensor, dst: Tensor, num_sample: Union[int, float] = 0.5,
+                                   src_padding_mask: Tensor = None, dst_padding_mask: Tensor = None):
         """P independent pairs in one call, no host sync.  src (P,Cd,M), dst (P,Cd,N) ->
         result (P,16) [R(9) T(3) rmse K' K'' iters], conf (P,2k) with the K'' inlier confidences first."""
         _C.require_cuda(src, dst)
         src, dst = self._prep(src), self._prep(dst)
         P, Cd, M = src.shape
         N = dst.shape[2]
+        sm, dm = self._mask(src_padding_mask, P, M, src.device), self._mask(dst_padding_mask, P, N, src.device)
         if dst.shape[0] != P or dst.shape[1] != Cd or Cd != self.in_channel + 3:
             raise ValueError("descriptors must be (P, in_channel+3, L) with matching P")
         k = self.num_pairs(num_sample, M, N)
@@ -175,9 +188,9 @@ class Decoder(nn.Module):
             _C.check(-1, "registration workspace")
         ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr(dev)}")
         with torch.cuda.device(dev):
-            rc = lib.dpm_registration_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(), P, M,
-                                              N, k, result.data_ptr(), conf.data_ptr(), ws.data_ptr(), ws.numel(),
-                                              _C.stream_ptr())
+            rc = lib.dpm_registration_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(),
+                                              _C.ptr(sm), _C.ptr(dm), P, M, N, k, result.data_ptr(), conf.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _C.stream_ptr())
         _C.check(rc, "registration_forward")
         return result, conf
 
@@ -186,13 +199,11 @@ class Decoder(nn.Module):
                              src_padding_mask: Tensor = None, dst_padding_mask: Tensor = None,
                              num_sample: Union[int, float] = 0.5) \
             -> Tuple[Tensor, Tensor, Tensor, Union[List[float], float]]:
-        if src_padding_mask is not None or dst_padding_mask is not None:
-            raise NotImplementedError("key padding masks are not used by the inference pipeline (always None)")
         batch = not (src_descriptor.ndim == 2 and dst_descriptor.ndim == 2)
         s = src_descriptor if batch else src_descriptor.unsqueeze(0)
         d = dst_descriptor if batch else dst_descriptor.unsqueeze(0)
         assert s.shape[0] == 1, 'batch size in inference must be 1'
-        result, conf = self.registration_forward_batch(s, d, num_sample)
+        result, conf = self.registration_forward_batch(s, d, num_sample, src_padding_mask, dst_padding_mask)
         host = result[0].cpu()  # the one sync the API demands (rmse is a Python float)
         R = result[0, _C.REG_R:_C.REG_R + 9].view(3, 3).clone()
         T = result[0, _C.REG_T:_C.REG_T + 3].view(3, 1).clone()
@@ -206,8 +217,6 @@ class Decoder(nn.Module):
     @torch.no_grad()
     def loop_detection_forward(self, src_descriptor: Tensor, dst_descriptor: Tensor,
                                src_padding_mask: Tensor = None, dst_padding_mask: Tensor = None) -> Tensor:
-        if src_padding_mask is not None or dst_padding_mask is not None:
-            raise NotImplementedError("key padding masks are not used by the inference pipeline (always None)")
         if src_descriptor.ndim == 2 and dst_descriptor.ndim == 2:
             src_descriptor, dst_descriptor = src_descriptor.unsqueeze(0), dst_descriptor.unsqueeze(0)
         _C.require_cuda(src_descriptor, dst_descriptor)
@@ -217,11 +226,13 @@ class Decoder(nn.Module):
         dev = src.device
         lib = _C.lib()
         warr, nw = self._weights(dev)
+        sm, dm = self._mask(src_padding_mask, P, M, dev), self._mask(dst_padding_mask, P, N, dev)
         prob = torch.empty((P,), dtype=torch.float32, device=dev)
         nb = lib.dpm_loop_detection_workspace_bytes(ctypes.byref(self._desc), P, M, N)
         ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr(dev)}")
         with torch.cuda.device(dev):
-            rc = lib.dpm_loop_detection_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(), P, M,
-                                                N, prob.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr())
+            rc = lib.dpm_loop_detection_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(),
+                                                _C.ptr(sm), _C.ptr(dm), P, M, N, prob.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _C.stream_ptr())
         _C.check(rc, "loop_detection_forward")
         return prob

@@ -213,8 +213,12 @@ typedef struct dpm_decoder_desc {
  *   result (P,DPM_REG_STRIDE) floats; conf_out (P,2k) = pairing confidence of the kept
  *   correspondences in reference order with the inlier ones FIRST COMPACTED:
  *   conf_out[p][0..K''-1] is what the reference returns. */
+/* src_pad (P,M) / dst_pad (P,N): the reference's key-padding masks (1 = padded descriptor, ignored as an attention
+ * KEY, descriptor_attention.py:33-42; like the reference the padded rows still take part in everything else), or
+ * NULL (shipped inference always passes None). */
 int dpm_registration_forward(const dpm_decoder_desc *desc, const float *const *weights,
-                             int n_weights, const float *src, const float *dst, int P, int M,
+                             int n_weights, const float *src, const float *dst,
+                             const uint8_t *src_pad, const uint8_t *dst_pad, int P, int M,
                              int N, int k, float *result, float *conf_out, void *ws,
                              size_t ws_bytes, dpm_stream_t stream);
 size_t dpm_registration_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N, int k);
@@ -222,7 +226,8 @@ size_t dpm_registration_workspace_bytes(const dpm_decoder_desc *desc, int P, int
 /* Decoder.loop_detection_forward, decoder.py:129-143 + OverlapHead heads.py:45-69:
  * src, dst (P,Cd,L) -> prob (P). */
 int dpm_loop_detection_forward(const dpm_decoder_desc *desc, const float *const *weights,
-                               int n_weights, const float *src, const float *dst, int P, int M,
+                               int n_weights, const float *src, const float *dst,
+                               const uint8_t *src_pad, const uint8_t *dst_pad, int P, int M,
                                int N, float *prob, void *ws, size_t ws_bytes, dpm_stream_t stream);
 size_t dpm_loop_detection_workspace_bytes(const dpm_decoder_desc *desc, int P, int M, int N);
 /* number of entries of `weights` for the decoder calls: the 82 state_dict tensors in

@@ -255,3 +255,35 @@ def test_loop_detection_batched_unsaturated(cfg, C, Ms, Ns):
     assert got.shape == (C,)
     assert float(want.min()) > 1e-3 and float(want.max()) < 1 - 1e-3, "test data saturates the sigmoid"
     assert (got.cpu() - want).abs().max() < TOL
+
+
+def test_key_padding_masks(cfg, checkpoint, golden_sample):
+    """MT-mode batches are padded (`padding_to`, system/core.py:141-169) and the decoder gets key-padding masks
+    (descriptor_attention.py:33-42): padded descriptors are ignored as attention keys and nowhere else."""
+    sd = checkpoint["decoder"]
+    dec = _dec(cfg, sd)
+    d0, d1 = torch.from_numpy(golden_sample["desc0"]), torch.from_numpy(golden_sample["desc1"])
+    g = torch.Generator().manual_seed(2)
+    sp = torch.zeros(256, dtype=torch.bool); sp[200:] = True                    # a padded tail ...
+    dp = torch.rand(256, generator=g) < 0.2                                     # ... and scattered padding
+    src, dst = d0.clone(), d1.clone()
+    src[:, sp] = 0.0
+    Rw, Tw, cw, rw = M.registration_forward(sd, cfg, src, dst, 0.5, s_pad=sp, d_pad=dp)
+    R, T, c, r = dec.registration_forward(src.to(DEV), dst.to(DEV), sp.to(DEV), dp.to(DEV), num_sample=0.5)
+    assert c.shape == cw.shape
+    assert (R.cpu() - Rw).abs().max() < TOL and (T.cpu() - Tw).abs().max() < TOL * max(1.0, float(Tw.abs().max()))
+    assert (c.cpu() - cw).abs().max() < TOL and abs(r - rw) < TOL * max(1.0, rw)
+    # the masks matter: without them the answer differs
+    R0, T0, c0, r0 = dec.registration_forward(src.to(DEV), dst.to(DEV), num_sample=0.5)
+    assert c0.shape != c.shape or (c0 - c).abs().max() > 1e-3
+    # loop head, batched, random weights (unsaturated), one side masked only
+    sdr = M.random_weights(M.decoder_shapes(cfg), seed=11)
+    decr = _dec(cfg, sdr)
+    S, D = _descs(31, 256, P=4), _descs(32, 192, P=4)
+    spm = torch.rand(4, 256, generator=g) < 0.3
+    want = M.loop_detection_forward(sdr, cfg, S, D, spm, None)
+    got = decr.loop_detection_forward(S.to(DEV), D.to(DEV), spm.to(DEV), None)
+    assert (got.cpu() - want).abs().max() < TOL
+    assert (decr.loop_detection_forward(S.to(DEV), D.to(DEV)).cpu() - want).abs().max() > 1e-5
+    with pytest.raises(ValueError):
+        dec.registration_forward(src.to(DEV), dst.to(DEV), sp[:100].to(DEV), None)

@@ -371,3 +371,22 @@ def test_outlier_filter_matches_reference():
     kept, mask, stat, thr = outlier_ref.outlier_filter(xyz, 10, 3.0)
     assert 0 < int((~mask).sum()) < 600
     assert torch.equal(out.xyz, kept)
+
+
+@needs_ref
+@pytest.mark.reference
+def test_decoder_key_padding_masks_match_reference(reference):
+    """the masks reach the attention only (descriptor_attention.py:33-42); restated in model_ref._mha"""
+    dec, sd = reference["dec"], reference["ck"]["decoder"]
+    cfg = M.default_config()
+    g = torch.Generator().manual_seed(5)
+    src, dst = torch.randn(131, 96, generator=g), torch.randn(131, 80, generator=g)
+    src[128:] *= 20; dst[128:] *= 20
+    sp, dp = torch.rand(96, generator=g) < 0.25, torch.rand(80, generator=g) < 0.25
+    with torch.no_grad():
+        R, T, c, r = dec.registration_forward(src, dst, sp.view(1, -1), dp.view(1, -1), num_sample=0.5)
+        lp = dec.loop_detection_forward(src[None], dst[None], sp.view(1, -1), dp.view(1, -1))
+    Rw, Tw, cw, rw = M.registration_forward(sd, cfg, src, dst, 0.5, s_pad=sp, d_pad=dp)
+    assert c.shape == cw.shape and (R - Rw).abs().max() < 1e-4 and (T - Tw).abs().max() < 1e-3 and (c - cw).abs().max() < 1e-4
+    lw = M.loop_detection_forward(sd, cfg, src[None], dst[None], sp.view(1, -1), dp.view(1, -1))
+    assert (lp - lw).abs().max() < 1e-5
