@@ -81,6 +81,8 @@ _SIGS = {
     "dpm_map_tile_f32": ([_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp], _i),
     "dpm_outlier_filter_workspace_bytes": ([_i, _i], _sz),
     "dpm_outlier_filter_f32": ([_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp], _i),
+    "dpm_low_pass_filter_workspace_bytes": ([_i, _i], _sz),
+    "dpm_low_pass_filter_f32": ([_vp, _i, _i, _f, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_kabsch_f32": ([_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
 }
 

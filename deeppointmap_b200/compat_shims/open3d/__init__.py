@@ -169,4 +169,4 @@ class _Pipelines:
 pipelines = _Pipelines()
 
 import sys as _sys
-open3d = _sys.modules[__name__]  # the reference spells `o3d.open3d.utility.Vector3dVector` (recoder.py:179)
+open3d = _sys.modules.get(__name__)  # the reference spells `o3d.open3d.utility.Vector3dVector` (recoder.py:179)

@@ -146,6 +146,9 @@ int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, 
 int knn_ring_launch(const GridWs &g, const float4 *q4, int B, int S, const int *qlen32, int K, int64_t *idx64,
                     int32_t *idx32, float *d2out, cudaStream_t st);
 
+// per-point surface normal from the neighbours within `radius` (grid cell size must be >= radius; g == nullptr: brute force)
+int radius_normals_launch(const GridWs *g, const float4 *q4, int S, float radius, float *normals, cudaStream_t st);
+
 // ---- internal launchers shared between translation units ------------------------------
 // xyz4 buffers are float4 (x,y,z,0) rows.
 int fps_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64,

@@ -775,6 +775,117 @@ int knn_ring_launch(const GridWs &g, const float4 *q4, int B, int S, const int *
     return DPM_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// surface normals from the points within a radius (open3d estimate_normals with KDTreeSearchParamRadius, as
+// LowPassFilter uses it, dataloader/transforms.py:269-272): covariance of the neighbours (the point itself
+// included), eigenvector of its smallest eigenvalue; fewer than 3 neighbours -> (0, 0, 1).  One warp per point over
+// the 3 x 3 x 3 cell block (cell size >= radius); moments are summed relative to the query in fp32 (|d| <= radius),
+// reduced and diagonalised in fp64 (cyclic Jacobi).  The sign of a normal is arbitrary, as in open3d without an
+// orientation step; its only consumer takes |n_i . n_j|.
+// ---------------------------------------------------------------------------------------
+__device__ void smallest_eigvec3(double a00, double a01, double a02, double a11, double a12, double a22, float *n) {
+    double A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+        if (off < 1e-30) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    int m = 0;
+    if (A[1][1] < A[m][m]) m = 1;
+    if (A[2][2] < A[m][m]) m = 2;
+    const double l = sqrt(V[0][m] * V[0][m] + V[1][m] * V[1][m] + V[2][m] * V[2][m]);
+    n[0] = (float)(V[0][m] / l); n[1] = (float)(V[1][m] / l); n[2] = (float)(V[2][m] / l);
+}
+
+template <bool GRID>
+__global__ void __launch_bounds__(KG_T)
+radius_normals_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted, const int *__restrict__ cell_start,
+                      const GridDesc *__restrict__ desc, int S, int N, float r2, float *__restrict__ normals) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (KG_T / 32) + (threadIdx.x >> 5);
+    if (s >= S) return;  // warp-uniform
+    const float4 c = q4[s];
+    float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cnt = 0;
+    auto take = [&](const float4 p) {
+        const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+        if (dx * dx + dy * dy + dz * dz <= r2) {
+            m[0] += dx; m[1] += dy; m[2] += dz;
+            m[3] += dx * dx; m[4] += dx * dy; m[5] += dx * dz; m[6] += dy * dy; m[7] += dy * dz; m[8] += dz * dz;
+            ++cnt;
+        }
+    };
+    if (GRID) {
+        const GridDesc d = desc[0];
+        const int cx = cell_coord_free(c.x, d.ox, d.inv_h, d.gx), cy = cell_coord_free(c.y, d.oy, d.inv_h, d.gy),
+                  cz = cell_coord_free(c.z, d.oz, d.inv_h, d.gz);
+        int rs = 0, re = 0;
+        if (lane < 9) {
+            const int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, d.gx - 1);
+            if (yy >= 0 && yy < d.gy && zz >= 0 && zz < d.gz && x0 <= x1) {
+                const int row = (zz * d.gy + yy) * d.gx;
+                rs = cell_start[row + x0];
+                re = cell_start[row + x1 + 1];
+            }
+        }
+        for (int r = 0; r < 9; ++r) {
+            const int b0 = __shfl_sync(0xffffffffu, rs, r), b1 = __shfl_sync(0xffffffffu, re, r);
+            for (int i = b0 + lane; i < b1; i += 32) take(sorted[i]);
+        }
+    } else {
+        for (int i = lane; i < N; i += 32) take(q4[i]);
+    }
+    double acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = warp_sum_d((double)m[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+        float n[3] = {0.f, 0.f, 1.f};
+        if (cnt >= 3) {
+            const double inv = 1.0 / (double)cnt;
+            const double mx = acc[0] * inv, my = acc[1] * inv, mz = acc[2] * inv;
+            smallest_eigvec3(acc[3] * inv - mx * mx, acc[4] * inv - mx * my, acc[5] * inv - mx * mz, acc[6] * inv - my * my,
+                             acc[7] * inv - my * mz, acc[8] * inv - mz * mz, n);
+        }
+        normals[(size_t)s * 3] = n[0]; normals[(size_t)s * 3 + 1] = n[1]; normals[(size_t)s * 3 + 2] = n[2];
+    }
+}
+
+// normals (S,3) of the cloud q4 (S points, one cloud); g == nullptr: no grid, every point is tested (small clouds)
+int radius_normals_launch(const GridWs *g, const float4 *q4, int S, float radius, float *normals, cudaStream_t st) {
+    if (S <= 0 || !(radius > 0.f)) return fail(DPM_ERR_SHAPE, "normals: bad arguments");
+    const float r2 = radius * radius;
+    dim3 grid((S + KG_T / 32 - 1) / (KG_T / 32), 1, 1);
+    if (g) radius_normals_kernel<true><<<grid, KG_T, 0, st>>>(q4, g->sorted, g->cell_start, g->desc, S, S, r2, normals);
+    else radius_normals_kernel<false><<<grid, KG_T, 0, st>>>(q4, nullptr, nullptr, nullptr, S, S, r2, normals);
+    DPM_CHECK_LAUNCH("normals", st);
+    return DPM_OK;
+}
+
 int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
                     int K, float r2, int64_t *idx64, int32_t *idx32, cudaStream_t st, bool pad) {
     if (B <= 0 || S <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "knn: bad shape B=%d S=%d N=%d", B, S, N);

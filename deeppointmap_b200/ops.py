@@ -174,17 +174,23 @@ def information_matrix(pointcloud_1: torch.Tensor, pointcloud_2: torch.Tensor, S
 
 
 def preprocess_frame(raw: torch.Tensor, voxel_size: float = 0.3, min_dis: float = 1.0, max_dis: float = 60.0,
-                     ratio: float = 60.0, max_voxels: int = 1 << 26, outlier=None) -> torch.Tensor:
+                     ratio: float = 60.0, max_voxels: int = 1 << 26, outlier=None, lowpass=None) -> torch.Tensor:
     """Raw frame -> encoder input on the device: BinReader's NaN-row drop, VoxelSample(voxel_size, 'first'),
     DistanceSample(min_dis, max_dis), [OutlierFilter(*outlier), e.g. outlier=(10, 3.0) as in the shipped YAML],
     CoordinatesNormalization(ratio) (dataloader/heads/bin.py:16-17, dataloader/transforms.py:230-246, 331-356,
     387-407).  raw (N, C>=3) CUDA fp32 rows (a KITTI .bin is (N,4)) -> (3, n) fp32, points in the reference's
     order (ascending voxel id).  One host sync per data-dependent size."""
-    if outlier is not None:
-        pts = preprocess_frame(raw, voxel_size, min_dis, max_dis, 1.0, max_voxels)        # metres (x / 1.0 is exact)
-        # pcd.xyz /= ratio as an IEEE division inside the filter's emit pass (torch's CUDA `/ scalar` multiplies by
-        # the reciprocal, which is 1 ulp off the reference's CPU arithmetic)
-        return outlier_filter(pts.T.contiguous(), int(outlier[0]), float(outlier[1]), out_divisor=float(ratio)).T.contiguous()
+    if outlier is not None or lowpass is not None:
+        # the whole shipped YAML chain on the device: VoxelSample -> DistanceSample -> [OutlierFilter(*outlier)] ->
+        # [LowPassFilter(*lowpass), e.g. lowpass=(0.5, 16, 2.0, 4)] -> CoordinatesNormalization
+        rows = preprocess_frame(raw, voxel_size, min_dis, max_dis, 1.0, max_voxels).T.contiguous()   # metres (x / 1.0 is exact)
+        # pcd.xyz /= ratio as an IEEE division inside the LAST filter's emit pass (torch's CUDA `/ scalar` multiplies
+        # by the reciprocal, which is 1 ulp off the reference's CPU arithmetic)
+        if outlier is not None:
+            rows = outlier_filter(rows, int(outlier[0]), float(outlier[1]), out_divisor=1.0 if lowpass is not None else float(ratio))
+        if lowpass is not None:
+            rows = low_pass_filter(rows, *lowpass, out_divisor=float(ratio))
+        return rows.T.contiguous()
     _C.require_cuda(raw)
     if raw.dim() != 2 or raw.shape[1] < 3:
         raise ValueError("raw must be (N, C>=3)")
@@ -262,4 +268,46 @@ def outlier_filter(rows: torch.Tensor, nb_neighbors: int = 10, std_ratio: float 
                                             mask.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(), _C.stream_ptr()),
                  "outlier_filter")
     kept = out[:int(cnt.item())]
+    return (kept, mask) if return_mask else kept
+
+
+def low_pass_filter(rows: torch.Tensor, normals_radius: float = 0.5, normals_num: int = 16, filter_std: float = 2.0,
+                    flux: int = 4, max_remain: int = -1, return_mask: bool = False, out_divisor: float = 1.0):
+    """LowPassFilter (dataloader/transforms.py:256-297) in one native call: rows (N, C>=3) CUDA fp32, metres ->
+    (n, 3) rows kept (original order, IEEE-divided by out_divisor) [, (N,) bool mask].  One host sync (n).
+    max_remain > 0 and smaller than the kept count: the reference then keeps the max_remain points of largest
+    similarity IN THAT ORDER (transforms.py:284-285) -- done here from the kernel's statistic."""
+    _C.require_cuda(rows)
+    if rows.dim() != 2 or rows.shape[1] < 3:
+        raise ValueError("rows must be (N, C>=3)")
+    r = _f32c(rows)
+    n, stride = r.shape
+    dev = r.device
+    if n == 0:
+        e = torch.empty((0, 3), dtype=torch.float32, device=dev)
+        return (e, torch.empty((0,), dtype=torch.bool, device=dev)) if return_mask else e
+    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((n,), dtype=torch.bool, device=dev)
+    sim = torch.empty((n,), dtype=torch.float32, device=dev)
+    cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+    lib = _C.lib()
+    nb = lib.dpm_low_pass_filter_workspace_bytes(n, int(normals_num))
+    if nb == 0:
+        raise NotImplementedError("normals_num must be in 1..31")
+    ws = _ws(dev, nb)
+    with torch.cuda.device(dev):
+        _C.check(lib.dpm_low_pass_filter_f32(r.data_ptr(), n, stride, float(normals_radius), int(normals_num),
+                                             float(filter_std), int(flux), float(out_divisor), out.data_ptr(),
+                                             mask.data_ptr(), sim.data_ptr(), cnt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             _C.stream_ptr()), "low_pass_filter")
+    k = int(cnt.item())
+    if 0 < int(max_remain) < k:
+        top = torch.topk(sim, k=int(max_remain)).indices
+        kept = r[top, :3] / float(out_divisor)
+        if return_mask:
+            m = torch.zeros((n,), dtype=torch.bool, device=dev)
+            m[top] = True
+            return kept, m
+        return kept
+    kept = out[:k]
     return (kept, mask) if return_mask else kept

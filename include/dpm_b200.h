@@ -298,6 +298,17 @@ int dpm_outlier_filter_f32(const float *rows, int N, int stride, int nb_neighbor
                            float out_divisor, float *out_rows, uint8_t *mask, int32_t *count, void *workspace,
                            size_t ws_bytes, dpm_stream_t stream);
 
+/* LowPassFilter (dataloader/transforms.py:256-297): rows (N x stride floats, xyz first, metres) -> the rows whose
+ * normal agrees with its neighbours': sim_i = sum of the `flux` largest |n_i . n_j| over the normals_num nearest
+ * neighbours j (n = PCA normal of the points within normals_radius, open3d's estimate_normals), kept when
+ * sim_i > mean(sim) - filter_std * std(sim); original order, divided by out_divisor.  out_rows: room for N x 3
+ * floats; mask (N bytes) and sim_out (N floats) optional; count (device int32) the number of survivors.
+ * normals_num <= 31, flux <= 8.  The reference's max_remain re-ranking is left to the caller (sim_out).  No host sync. */
+size_t dpm_low_pass_filter_workspace_bytes(int N, int normals_num);
+int dpm_low_pass_filter_f32(const float *rows, int N, int stride, float normals_radius, int normals_num,
+                            float filter_std, int flux, float out_divisor, float *out_rows, uint8_t *mask,
+                            float *sim_out, int32_t *count, void *workspace, size_t ws_bytes, dpm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,3 +390,31 @@ def test_decoder_key_padding_masks_match_reference(reference):
     assert c.shape == cw.shape and (R - Rw).abs().max() < 1e-4 and (T - Tw).abs().max() < 1e-3 and (c - cw).abs().max() < 1e-4
     lw = M.loop_detection_forward(sd, cfg, src[None], dst[None], sp.view(1, -1), dp.view(1, -1))
     assert (lp - lw).abs().max() < 1e-5
+
+
+@needs_ref
+@pytest.mark.reference
+def test_low_pass_filter_matches_reference():
+    """oracle/lowpass_ref.py vs the reference's LowPassFilter class (transforms.py:256-297) run on CPU: open3d is the
+    numpy / scipy stand-in of compat_shims (the same normal algorithm the oracle restates), knn_points / knn_gather are
+    plain-torch stand-ins of the pytorch3d contract.  Same rows kept."""
+    import importlib
+    from oracle import frontend_ref, lowpass_ref
+    from ref_infomat import _cpu_knn_points
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "dpm_open3d_shim", os.path.join(ROOT, "deeppointmap_b200", "compat_shims", "open3d", "__init__.py"))
+    shim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shim)
+    shim.open3d = shim                          # the reference spells o3d.open3d.utility (transforms.py:270)
+    RT = _reference_transforms()
+    RT.o3d = shim
+    RT.has_t3d, RT.knn_points = True, _cpu_knn_points
+    RT.knn_gather = lambda x, idx: x[0][idx[0]][None]           # (1,N,C), (1,N,K) -> (1,N,K,C)
+    raw = np.fromfile(f"{REF}/data/sample/seq06/velodyne/000004.bin", dtype=np.float32).reshape(-1, 4)
+    xyz = (frontend_ref.preprocess_bin(raw) * 60.0).T.contiguous()[:5000]     # metres, after voxel + distance sampling
+    pcd = RT.PointCloud(xyz.numpy().copy())
+    out = RT.LowPassFilter(normals_radius=0.5, normals_num=16, filter_std=2.0, flux=4, max_remain=-1)(pcd)
+    kept, mask, sim, thr = lowpass_ref.low_pass_filter(xyz, 0.5, 16, 2.0, 4)
+    assert 0 < int((~mask).sum()) < 1500
+    assert torch.equal(out.xyz, kept)
