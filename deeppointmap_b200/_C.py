@@ -74,6 +74,7 @@ _SIGS = {
     "dpm_decoder_num_weights": ([ctypes.POINTER(DecoderDesc)], _i),
     "dpm_posenc_f32": ([_vp, _i, _vp, _i, _vp, _i, _i, _vp], _i),
     "dpm_attention_f32": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp], _i),
+    "dpm_attention_pairs_f32": ([_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
     "dpm_information_matrix_workspace_bytes": ([_i, _i], _sz),
     "dpm_information_matrix_f32": ([_vp, _i, _vp, _i, _vp, _f, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_frontend_workspace_bytes": ([_ll], _sz),

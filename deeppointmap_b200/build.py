@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libdpm_b200.so")
-SOURCES = ["core.cu", "fps.cu", "fps_cluster.cu", "knn.cu", "grid.cu", "dense.cu", "gemm_tc.cu", "encoder.cu", "decoder.cu", "pairing.cu", "infomat.cu", "frontend.cu", "maptile.cu", "outlier.cu", "lowpass.cu"]
+SOURCES = ["core.cu", "fps.cu", "fps_cluster.cu", "knn.cu", "grid.cu", "dense.cu", "gemm_tc.cu", "encoder.cu", "decoder.cu", "attention_tc5.cu", "pairing.cu", "infomat.cu", "frontend.cu", "maptile.cu", "outlier.cu", "lowpass.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 

@@ -194,6 +194,9 @@ int group_from_xyz_launch(const float *Wsa, int ldw, const float *bias, const fl
                           float4 *comp, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *gamma,
                           const float *beta, float radius, float *out, int B, int N, int S, int K, int Cout,
                           cudaStream_t st);
+// attention_tc5.cu: tcgen05 flash attention for long key ranges (pairs layout of decoder.cu)
+int attention_tc5_launch(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out, int ldo,
+                         int P, int M, int N, int mode, int heads, const uint8_t *kmask, cudaStream_t st);
 // pairing.cu: dual softmax + global top-k of the similarity matrices, three launches
 constexpr int PAIR_MAXK = 4096;
 size_t pairing_ws_bytes(int P);

@@ -7,6 +7,8 @@
 // self/cross attention are one launch over 2P (query-range, key-range) problems.
 // Data-dependent shapes of the reference (offset filter, sigma clipping) are restated with
 // counts + masks on the device: there is no host sync anywhere in here.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dpm {
@@ -293,6 +295,10 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
                      const uint8_t *kmask = nullptr) {
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
     if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
+    // long key ranges (map tiles): flash attention on tcgen05 / TMEM (attention_tc5.cu); DPM_ATT_IMPL=1 keeps mma.sync
+    static const int impl_env = getenv("DPM_ATT_IMPL") ? atoi(getenv("DPM_ATT_IMPL")) : 0;
+    if (!prob && impl_env != 1 && (M > 512 || N > 512 || impl_env == 2))
+        return attention_tc5_launch(q, ldq, k, ldk, v, ldv, out, ldo, nprob / 2, M, N, mode, heads, kmask, st);
     dim3 grid((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
     // the longest key range of the launch decides (prob == nullptr: the two sides of the pairs; else the caller's table,
     // which this host code cannot read: the accurate variant then)
@@ -897,6 +903,23 @@ extern "C" int dpm_attention_f32(const float *q, int ldq, const float *k, int ld
                                  int ldo, const int *prob, int nprob, int max_lq, int heads, dpm_stream_t stream) {
     if (!q || !k || !v || !out || !prob) return fail(DPM_ERR_ARG, "attention: null pointer");
     return attention_launch(q, ldq, k, ldk, v, ldv, out, ldo, prob, nprob, max_lq, 0, 0, 0, heads, (cudaStream_t)stream);
+}
+
+/* the attention core in the decoder's own layout: P pairs, rows p*(M+N).. = M src then N dst tokens; mode 0 self,
+ * 1 cross; kmask optional (P*(M+N) bytes); impl 0 = as the decoder chooses, 1 = mma.sync kernel, 2 = tcgen05 kernel */
+extern "C" int dpm_attention_pairs_f32(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv,
+                                       float *out, int ldo, int P, int M, int N, int mode, int heads,
+                                       const uint8_t *kmask, int impl, dpm_stream_t stream) {
+    if (!q || !k || !v || !out) return fail(DPM_ERR_ARG, "attention: null pointer");
+    if (P <= 0 || M <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
+    if (impl == 2) return attention_tc5_launch(q, ldq, k, ldk, v, ldv, out, ldo, P, M, N, mode, heads, kmask, (cudaStream_t)stream);
+    if (impl == 1) {
+        dim3 grid(((M > N ? M : N) + AT_BQ - 1) / AT_BQ, heads, 2 * P);
+        attention_tc_kernel<true><<<grid, AT_T, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, out, ldo, nullptr, M, N, mode, kmask);
+        DPM_CHECK_LAUNCH("attention", (cudaStream_t)stream);
+        return DPM_OK;
+    }
+    return attention_launch(q, ldq, k, ldk, v, ldv, out, ldo, nullptr, 2 * P, M > N ? M : N, M, N, mode, heads, (cudaStream_t)stream, kmask);
 }
 
 extern "C" int dpm_kabsch_f32(const float *src, const float *dst, const float *w, const int32_t *count, int P, int ldk,

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc5.cuh"
 
 namespace dpm {
 
@@ -31,91 +32,6 @@ constexpr int BM = 128;
 constexpr int BK = 32;            // fp32 elements per K block = one 128-byte swizzle row
 constexpr int THREADS = 288;      // 8 producer/epilogue warps + 1 MMA warp
 constexpr int A_TILE = BM * 128;  // bytes of one 128 x 32 fp32 tile
-
-__device__ __forceinline__ unsigned s32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void mma_tf32(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc,
-                                         unsigned idesc, unsigned accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit(unsigned bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
-    unsigned r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
-// >> 4 in [0,14), leading byte offset (unused for swizzled K-major: 1) in [16,30), stride byte
-// offset = 8 rows x 128 B = 1024 >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in
-// [61,64).  The tile base must be 1024-byte aligned.
-__device__ __forceinline__ unsigned long long smem_desc(unsigned saddr) {
-    return (unsigned long long)((saddr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1) at [4,6), A = B = TF32
-// (2) at [7,10) / [10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr unsigned instr_desc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
-}
-
-__device__ __forceinline__ float tf32_rna(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-// byte offset of 16-byte chunk c (0..7) of row r inside a K-major SWIZZLE_128B tile
-__device__ __forceinline__ unsigned swz(int r, int c) {
-    return (unsigned)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ r) & 7) << 4));
-}
 
 template <int ROWS>
 __device__ __forceinline__ void produce_tile(const float *__restrict__ G, int ld, int rows_total, int r0, int K, int k0,

@@ -250,6 +250,15 @@ int dpm_posenc_f32(const float *xyz, int ldx, const float *dim_t, int npf, float
 int dpm_attention_f32(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv,
                       float *out, int ldo, const int *prob /* device, nprob x 4: q0,Lq,k0,Lk */,
                       int nprob, int max_lq, int heads, dpm_stream_t stream);
+/* The attention core of DescriptorAttentionLayer (network/decoder/descriptor_attention.py:33-42, head_dim 32) in the
+ * decoder's token layout: P pairs, rows p*(M+N) .. p*(M+N)+M-1 are the src tokens, the next N the dst tokens; q / k / v
+ * (rows x heads*32, leading dimensions ldq / ldk / ldv) already projected.  mode 0: self attention of each side,
+ * 1: cross attention (src queries over dst keys and vice versa).  kmask: key-padding mask per token row or NULL.
+ * impl 0: as the decoder chooses (mma.sync for <= 512 keys, tcgen05 flash attention above), 1 / 2 force one. */
+int dpm_attention_pairs_f32(const float *q, int ldq, const float *k, int ldk, const float *v, int ldv, float *out,
+                            int ldo, int P, int M, int N, int mode, int heads, const uint8_t *kmask, int impl,
+                            dpm_stream_t stream);
+
 /* weighted Kabsch + 3-sigma loop, decoder.py:227-265, for P problems of Kc <= ldk
  * correspondences each: src/dst (P,3,ldk), w (P,ldk), count (P) int32 -> result
  * (P,DPM_REG_STRIDE), inlier mask (P,ldk) bytes (optional), conf_out (P,ldk) = the inlier

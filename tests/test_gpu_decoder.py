@@ -287,3 +287,31 @@ def test_key_padding_masks(cfg, checkpoint, golden_sample):
     assert (decr.loop_detection_forward(S.to(DEV), D.to(DEV)).cpu() - want).abs().max() > 1e-5
     with pytest.raises(ValueError):
         dec.registration_forward(src.to(DEV), dst.to(DEV), sp[:100].to(DEV), None)
+
+
+@pytest.mark.parametrize("Mq,Nk,mode", [(4096, 256, 0), (4096, 256, 1), (1000, 1500, 1), (130, 700, 0), (4096, 4096, 1)])
+@pytest.mark.parametrize("impl", [1, 2])
+def test_attention_pairs_long(Mq, Nk, mode, impl):
+    """both attention kernels (1: mma.sync with fresh per-tile accumulators, 2: tcgen05 / TMEM flash attention) on the
+    decoder's pair layout at map sizes, against fp64; with and without a key-padding mask"""
+    g = torch.Generator().manual_seed(Mq + Nk + mode)
+    H, R = 8, Mq + Nk
+    q, k, v = (torch.randn(R, 256, generator=g) for _ in range(3))
+    mask = torch.rand(R, generator=g) < 0.1
+    for km in (None, mask):
+        def ref(qs, ks, vs, kmask):
+            qq, kk, vv = (t.view(-1, H, 32).transpose(0, 1).double() for t in (qs, ks, vs))
+            att = qq @ kk.transpose(1, 2) / math.sqrt(32)
+            if kmask is not None:
+                att = att.masked_fill(kmask.view(1, 1, -1), float("-inf"))
+            return (torch.softmax(att, -1) @ vv).transpose(0, 1).reshape(-1, 256)
+        src, dst = slice(0, Mq), slice(Mq, R)
+        ksrc, kdst = (dst, src) if mode else (src, dst)
+        want = torch.cat([ref(q[src], k[ksrc], v[ksrc], None if km is None else km[ksrc]),
+                          ref(q[dst], k[kdst], v[kdst], None if km is None else km[kdst])])
+        qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
+        out = torch.full((R, 256), float("nan"), device=DEV)
+        kmd = None if km is None else km.to(DEV).to(torch.uint8)
+        _C.check(_C.lib().dpm_attention_pairs_f32(qd.data_ptr(), 256, kd.data_ptr(), 256, vd.data_ptr(), 256, out.data_ptr(), 256,
+                                                  1, Mq, Nk, mode, H, _C.ptr(kmd), impl, _C.stream_ptr()))
+        assert rel_err(out, want) < 3e-6, (impl, km is not None, rel_err(out, want))
