@@ -295,9 +295,10 @@ int attention_launch(const float *q, int ldq, const float *k, int ldk, const flo
                      const uint8_t *kmask = nullptr) {
     if (nprob <= 0 || heads <= 0 || maxLq <= 0) return fail(DPM_ERR_SHAPE, "attention: bad shape");
     if ((ldq | ldk | ldv | ldo) & 3) return fail(DPM_ERR_UNSUPPORTED, "attention: leading dimensions must be multiples of 4");
-    // long key ranges (map tiles): flash attention on tcgen05 / TMEM (attention_tc5.cu); DPM_ATT_IMPL=1 keeps mma.sync
+    // the decoder's pairs: flash attention on tcgen05 / TMEM (attention_tc5.cu) at every size -- 2.2x this kernel on map
+    // tiles, 1.3x on the 256-descriptor odometry pairs (0.61 -> 0.47 ms per 32-pair step).  DPM_ATT_IMPL=1 keeps mma.sync.
     static const int impl_env = getenv("DPM_ATT_IMPL") ? atoi(getenv("DPM_ATT_IMPL")) : 0;
-    if (!prob && impl_env != 1 && (M > 512 || N > 512 || impl_env == 2))
+    if (!prob && impl_env != 1)
         return attention_tc5_launch(q, ldq, k, ldk, v, ldv, out, ldo, nprob / 2, M, N, mode, heads, kmask, st);
     dim3 grid((maxLq + AT_BQ - 1) / AT_BQ, heads, nprob);
     // the longest key range of the launch decides (prob == nullptr: the two sides of the pairs; else the caller's table,

@@ -289,7 +289,8 @@ def test_key_padding_masks(cfg, checkpoint, golden_sample):
         dec.registration_forward(src.to(DEV), dst.to(DEV), sp[:100].to(DEV), None)
 
 
-@pytest.mark.parametrize("Mq,Nk,mode", [(4096, 256, 0), (4096, 256, 1), (1000, 1500, 1), (130, 700, 0), (4096, 4096, 1)])
+@pytest.mark.parametrize("Mq,Nk,mode", [(4096, 256, 0), (4096, 256, 1), (1000, 1500, 1), (130, 700, 0), (4096, 4096, 1),
+                                        (256, 256, 1), (100, 37, 0), (33, 65, 1), (1, 5, 1)])
 @pytest.mark.parametrize("impl", [1, 2])
 def test_attention_pairs_long(Mq, Nk, mode, impl):
     """both attention kernels (1: mma.sync with fresh per-tile accumulators, 2: tcgen05 / TMEM flash attention) on the
