@@ -48,11 +48,8 @@ __device__ __forceinline__ void produce_tile(const float *__restrict__ G, int ld
 #pragma unroll
     for (int i = 0; i < ITER; ++i) {
         const int idx = tid + i * 128, r = idx >> 3, c = idx & 7;
-        float4 h, l;
-        h.x = tf32_rna(v[i].x); l.x = tf32_rna(v[i].x - h.x);
-        h.y = tf32_rna(v[i].y); l.y = tf32_rna(v[i].y - h.y);
-        h.z = tf32_rna(v[i].z); l.z = tf32_rna(v[i].z - h.z);
-        h.w = tf32_rna(v[i].w); l.w = tf32_rna(v[i].w - h.w);
+        float4 h, l;  // Veltkamp split on the FP32 pipe (cvt.rna.tf32 is a quarter-rate conversion), see tc5.cuh
+        split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
         const unsigned off = swz(r, c);
         *reinterpret_cast<float4 *>(hi + off) = h;
         *reinterpret_cast<float4 *>(lo + off) = l;
