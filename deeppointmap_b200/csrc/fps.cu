@@ -218,7 +218,7 @@ int fps_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_
     if (B <= 0 || N <= 0 || K <= 0) return fail(DPM_ERR_SHAPE, "fps: bad shape B=%d N=%d K=%d", B, N, K);
     if ((long long)N > 16LL * FPS_T * 16)
         return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the register-resident limit %d", N, 16 * FPS_T * 16);
-    if (N <= FPS_BRUTE_CLUSTER_MAX_N && fps_cluster_mode(B))
+    if (N <= FPS_BRUTE_CLUSTER_MAX_N && fps_cluster_mode_small(B))
         return fps_brute_cluster_launch(xyz4, B, N, len32, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
     int P, CS;
     fps_pick(N, B, &P, &CS);
@@ -296,7 +296,7 @@ extern "C" int dpm_fps_f32(const float *points, int B, int N, int D, const int64
     int *len32 = a.get<int>(B);
     DPM_TRY(pack_xyz4_launch(points, B, N, D, xyz4, st));
     DPM_TRY(lengths_to_i32_launch(lengths, B, N, len32, st));
-    const bool brute = N <= FPS_BRUTE_CLUSTER_MAX_N && fps_cluster_mode(B);
+    const bool brute = N <= FPS_BRUTE_CLUSTER_MAX_N && fps_cluster_mode_small(B);
     if (N >= GRID_MIN_N && N <= GRID_MAX_N && !brute) {
         GridWs g;
         if (!grid_ws_carve(a, B, N, &g)) return fail(DPM_ERR_WORKSPACE, "fps: workspace too small");

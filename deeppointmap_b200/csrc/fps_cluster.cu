@@ -601,6 +601,21 @@ bool fps_cluster_mode(int B) {
     return B <= fps_cluster_capacity();
 }
 
+// clouds of <= FPS_BRUTE_CLUSTER_MAX_N points (every level below the first): the register-resident cluster kernel needs
+// no shared-memory tiles, so 16 of its CTAs fit on an SM and a whole batch of clusters is co-resident
+bool fps_cluster_mode_small(int B) {
+    static const char *env = getenv("DPM_FPS_MODE");
+    static const char *env_small = getenv("DPM_FPS_SMALL_MAXB");
+    int mode = g_fps_mode.load(std::memory_order_relaxed);
+    if (mode == 0 && env) mode = atoi(env);
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    // measured at 32 clouds per step: 256 light cluster CTAs instead of 32 one-SM CTAs halve the level-1 FPS (0.78 -> 0.40 ms)
+    // but crowd the other streams' kernels: 6778 -> 6450 frames/s.  So the default is the same bound as the big clouds'.
+    const int maxb = env_small ? atoi(env_small) : 0;
+    return B <= (maxb > fps_cluster_capacity() ? maxb : fps_cluster_capacity());
+}
+
 template <typename Kern, typename... Args>
 static int fc_launch(Kern kern, size_t smem, int B, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
