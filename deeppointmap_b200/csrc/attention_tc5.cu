@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 attention_tc5_kernel(const float *__restrict__ Q, int ldq, const float *__restrict__ Kp, int ldk,
                      const float *__restrict__ Vp, int ldv, float *__restrict__ O, int ldo, int M, int N, int mode,
                      const uint8_t *__restrict__ kmask) {
-    extern __shared__ unsigned char at5_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)at5_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem[];  // used directly: the compiler keeps the shared address space
     unsigned char *sQ = smem, *sK = smem + OFF_K, *sV = smem + OFF_V;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + OFF_MISC);       // 14 mbarriers
     unsigned &tmem_base_s = *reinterpret_cast<unsigned *>(smem + OFF_MISC + 120);

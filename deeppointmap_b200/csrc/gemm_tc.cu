@@ -140,8 +140,9 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
     if (res) res += (size_t)blockIdx.z * sY;
     constexpr int B_TILE = BN * 128;
     constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte aligned by declaration (SWIZZLE_128B atoms); used directly so that the compiler keeps the shared
+    // address space (an integer round trip to align it by hand turned every staging store into a generic ST)
+    extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
     __shared__ unsigned tmem_base_s;
 
