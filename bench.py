@@ -419,7 +419,8 @@ def reference_gpu_leg(cfg, dev, n, pts2):
 
 def pipeline_leg(n_synth, n_points, dev):
     """BASELINE configs[4]: the reference's own pipeline/infer.py, unmodified, on the drop-in modules -- over
-    `n_synth` synthetic KITTI-shape .bin scans (SURVEY 8d's config-5 generator) and over the reference's real sample
+    `n_synth` synthetic 65 536-point .bin scans (a street world: undulating ground, kerbs, facades with recesses, poles,
+    trees, parked boxes, seen from a 1 m / frame trajectory) and over the reference's real sample
     scans (51 frames forth and back) when they travelled.  frames/s from the reference's own per-stage timers
     (ResultLogger.log_time) and as whole-process wall clock (interpreter start, checkpoint load, file IO included)."""
     import shutil
@@ -436,7 +437,7 @@ def pipeline_leg(n_synth, n_points, dev):
         if n_synth > 0:
             seq = os.path.join(work, "synth", "0")
             pipeline.write_synthetic_sequence(seq, n_synth, n_points, seed=5, device=dev)
-            jobs.append(("synthetic", seq, n_synth, {"edge_confidence_drop": 0.0, "edge_rmse_drop": 1e9}))
+            jobs.append(("synthetic", seq, n_synth, None))   # shipped thresholds: the mapping thread drops the scans it distrusts
         real = ref_loader.sample_frames()
         if len(real) >= 2:
             seq = os.path.join(work, "real", "0")

@@ -43,7 +43,8 @@ DEFAULT_TRANSFORMS = {
 }
 
 
-def write_synthetic_sequence(out_dir: str, n_frames: int, n_points: int = 65536, seed: int = 0, device="cpu"):
+def write_synthetic_sequence(out_dir: str, n_frames: int, n_points: int = 65536, seed: int = 0, device="cpu",
+                             world: str = "street"):
     """`n_frames` KITTI-style scans `<i>.bin` (float32 (N,4): x, y, z in metres, intensity 0) of a synthetic corridor
     world seen from a smooth SE(2) trajectory (1 m per frame, yaw rate <= 2 deg per frame).  Returns the ground-truth
     poses (n,4,4) fp64."""
@@ -52,7 +53,8 @@ def write_synthetic_sequence(out_dir: str, n_frames: int, n_points: int = 65536,
     from . import sequence
     os.makedirs(out_dir, exist_ok=True)
     gt = sequence.trajectory(n_frames)
-    world = sequence.corridor_world(seed, length_m=float(gt[-1, 0, 3]) + 1.0, device=device)
+    make = sequence.street_world if world == "street" else sequence.corridor_world
+    world = make(seed, length_m=float(gt[-1, 0, 3]) + 1.0, device=device)
     for i0 in range(0, n_frames, 64):
         fr = sequence.corridor_frames(world, gt[i0:i0 + 64], n_points, seed=seed * 7919 + i0, scale=1.0, stable=True)  # metres
         for j in range(fr.shape[0]):

@@ -38,6 +38,70 @@ def corridor_world(seed: int, length_m: float, half_width_m: float = 70.0, groun
     return torch.cat([ground, facade], dim=1).to(device=device, dtype=torch.float32).contiguous()
 
 
+def street_world(seed: int, length_m: float, half_width_m: float = 60.0, device="cpu") -> torch.Tensor:
+    """(3, P) fp32 world points in metres with the kind of structure a street scan has, for runs where the trained
+    network has to register consecutive scans well (the reference's whole pipeline): a gently undulating ground sampled
+    on a jittered lattice, kerbs along the road, building facades with window recesses, poles, parked boxes and tree
+    crowns.  Deterministic in `seed`."""
+    g = torch.Generator().manual_seed(int(seed))
+    L = float(length_m) + 140.0
+    u = lambda *shape: torch.rand(*shape, generator=g)
+    parts = []
+    # ground: 0.35 m lattice + jitter, low-frequency height field
+    gx = torch.arange(-70.0, L - 70.0, 0.35)
+    gy = torch.arange(-half_width_m, half_width_m, 0.35)
+    X, Y = torch.meshgrid(gx, gy, indexing="ij")
+    X = X.flatten() + 0.1 * (u(X.numel()) - 0.5)
+    Y = Y.flatten() + 0.1 * (u(Y.numel()) - 0.5)
+    Z = -1.73 + 0.15 * torch.sin(X / 9.0) * torch.cos(Y / 7.0) + 0.05 * torch.sin(X / 2.3 + Y / 3.1)
+    parts.append(torch.stack([X, Y, Z]))
+    # kerbs: two 12 cm steps along the road
+    for side in (-1.0, 1.0):
+        kx = torch.arange(-70.0, L - 70.0, 0.05)
+        for dz in (0.0, 0.06, 0.12):
+            parts.append(torch.stack([kx, torch.full_like(kx, side * 4.0), torch.full_like(kx, -1.73 + dz)]))
+    # facades: rectangles 6-25 m long, 4-12 m high, with window recesses every 3 m
+    nb = max(4, int(L / 100.0 * 14))
+    for i in range(nb):
+        cx = float(u(1)) * L - 70.0
+        side = 1.0 if i % 2 == 0 else -1.0
+        cy = side * (9.0 + 18.0 * float(u(1)))
+        ln, ht = 6.0 + 19.0 * float(u(1)), 4.0 + 8.0 * float(u(1))
+        yaw = (float(u(1)) - 0.5) * 0.5
+        a = torch.arange(-ln / 2, ln / 2, 0.12)
+        h = torch.arange(0.0, ht, 0.12)
+        A, H = torch.meshgrid(a, h, indexing="ij")
+        A, H = A.flatten(), H.flatten()
+        recess = (((A + ln) % 3.0) < 1.2) & (((H % 3.0) > 1.0) & ((H % 3.0) < 2.4))
+        depth = torch.where(recess, torch.full_like(A, 0.25 * side), torch.zeros_like(A))
+        parts.append(torch.stack([cx + A * math.cos(yaw) - depth * math.sin(yaw), cy + A * math.sin(yaw) + depth * math.cos(yaw), -1.73 + H]))
+    # poles and tree trunks + crowns
+    npole = max(8, int(L / 100.0 * 30))
+    for i in range(npole):
+        px, py = float(u(1)) * L - 70.0, (1.0 if i % 2 else -1.0) * (4.5 + 10.0 * float(u(1)))
+        hgt = 3.0 + 5.0 * float(u(1))
+        z = torch.arange(0.0, hgt, 0.04)
+        th = u(z.numel()) * 2 * math.pi
+        parts.append(torch.stack([px + 0.12 * torch.cos(th), py + 0.12 * torch.sin(th), -1.73 + z]))
+        if i % 3 == 0:
+            n = 1500
+            d = torch.randn(3, n, generator=g)
+            d = d / d.norm(dim=0, keepdim=True) * (1.2 + 0.8 * u(n))
+            parts.append(torch.stack([px + d[0], py + d[1], -1.73 + hgt + d[2].abs()]))
+    # parked boxes (cars): 4.2 x 1.8 x 1.5 m
+    ncar = max(6, int(L / 100.0 * 16))
+    for i in range(ncar):
+        bx, by = float(u(1)) * L - 70.0, (1.0 if i % 2 else -1.0) * (2.9 + 0.4 * float(u(1)))
+        n = 2500
+        f = torch.randint(0, 5, (n,), generator=g)
+        a_, b_, c_ = u(n) - 0.5, u(n) - 0.5, u(n)
+        x = torch.where(f == 0, torch.full_like(a_, -0.5), torch.where(f == 1, torch.full_like(a_, 0.5), a_)) * 4.2
+        y = torch.where(f == 2, torch.full_like(b_, -0.5), torch.where(f == 3, torch.full_like(b_, 0.5), b_)) * 1.8
+        z = torch.where(f == 4, torch.ones_like(c_), c_) * 1.5
+        parts.append(torch.stack([bx + x, by + y, -1.73 + z]))
+    return torch.cat(parts, dim=1).to(device=device, dtype=torch.float32).contiguous()
+
+
 def trajectory(n_frames: int, step_m: float = 1.0, max_yaw_deg: float = 2.0) -> torch.Tensor:
     """(n,4,4) fp64 sensor poses in the world: `step_m` per frame along a gently weaving heading."""
     poses, x, y, yaw = [], 0.0, 0.0, 0.0

@@ -167,3 +167,35 @@ def test_fp_interp(B, N, S, C1, C2):
     _C.check(_C.lib().dpm_fp_interp_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), d_.data_ptr(), 0, out.data_ptr(), B, N, S, C1,
                                         C2, _C.stream_ptr()))
     assert rel_err(out, ref) < 2e-5
+
+
+def test_fp_interp_vs_reference_formula_on_coincident_points():
+    """FeaturePropagation (pointnext.py / model_ref._feature_propagation) ranks the 3-NN and forms the
+    weights from the EXPANDED distance -2ab + |a|^2 + |b|^2 before clamp(min=1e-8); the kernel uses direct differences.
+    Every coarse point coincides with a fine point (FPS picks a subset): there the kernel's d2 is exactly 0 (weight 1e8)
+    while the expanded form leaves a rounding residue of up to ~1e-7 (weight >= 1e7).  The other two neighbours weigh
+    ~1e2..1e3, so the two conventions differ by at most ~5e-5 of the neighbour-feature spread -- inside the 1e-4 bar,
+    and pinned here on exactly those rows against the reference formula evaluated in fp32."""
+    from oracle import model_ref as M
+    g = torch.Generator().manual_seed(4)
+    B, N, S, C1, C2 = 2, 1024, 256, 64, 128
+    x1 = torch.rand(B, N, 3, generator=g) * 2 - 1            # normalised coordinates, like the encoder's
+    x2 = x1[:, :S].clone()                                   # the coarse level: a subset of the fine level
+    f1, f2 = torch.randn(B, N, C1, generator=g), torch.randn(B, S, C2, generator=g)
+    d = M._coordinate_distance(x1, x2)                       # the reference's expanded form, fp32
+    dd, idx = torch.topk(d, k=3, dim=-1, largest=False)
+    w = 1.0 / dd.clamp(min=1e-8)
+    w = w / w.sum(dim=2, keepdim=True)
+    want = (M._gather_rows(f2, idx) * w.unsqueeze(-1)).sum(dim=2)
+
+    def f4(t):
+        return torch.cat([t, torch.zeros(*t.shape[:-1], 1)], -1).contiguous().to(DEV)
+
+    out = torch.empty(B, N, C1 + C2, device=DEV)
+    a, b, c, d_ = f4(x1), f4(x2), f1.to(DEV), f2.to(DEV)
+    _C.check(_C.lib().dpm_fp_interp_f32(a.data_ptr(), b.data_ptr(), c.data_ptr(), d_.data_ptr(), 0, out.data_ptr(), B, N, S, C1,
+                                        C2, _C.stream_ptr()))
+    got = out.cpu()[:, :, C1:]
+    coincident = got[:, :S], want[:, :S]
+    assert rel_err(*coincident) < 1e-4
+    assert torch.equal(out.cpu()[:, :, :C1], f1)

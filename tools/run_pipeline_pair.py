@@ -43,8 +43,7 @@ if __name__ == "__main__":
     out = {}
     for impl in ("b200", "reference"):
         y = pipeline.write_yaml(os.path.join(work, f"cfg_{impl}.yaml"), ref, [seq], os.path.join(work, f"out_{impl}"),
-                                transforms=pipeline.MINIMAL_TRANSFORMS,
-                                slam_overrides={"edge_confidence_drop": 0.0, "edge_rmse_drop": 1e9} if gt is not None else None)
+                                transforms=pipeline.MINIMAL_TRANSFORMS)
         dt = run(impl, ref, y, weight, os.path.join(work, f"log_{impl}.txt"))
         out[impl] = load_traj(os.path.join(work, f"out_{impl}"))
         print(f"{impl}: {n} frames in {dt:.1f} s wall (process start, model load, data loading and SLAM bookkeeping included) = {n / dt:.2f} frames/s; {len(out[impl][0])} scans in the trajectory")
