@@ -138,6 +138,8 @@ bool fps_cluster_mode(int B);
 bool fps_cluster_mode_small(int B);  // for clouds of <= FPS_BRUTE_CLUSTER_MAX_N points
 int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                             float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);
+int fps_grid_onesm_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
+                          float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);
 int fps_brute_cluster_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64, int32_t *idx32,
                              float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);
 int knn_grid_launch(const GridWs &g, const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,

@@ -32,19 +32,26 @@
 
 namespace dpm {
 
-constexpr int FC_CS = 8;                  // CTAs per cloud
-constexpr int FC_WPC = 4;                 // warps per CTA: one per scheduler
-constexpr int FC_T = FC_WPC * 32;
-constexpr int FC_NW = FC_CS * FC_WPC;     // warps per cloud = records per pick (one per lane of the reducing warp)
-static_assert(FC_NW == 32, "the record reduce takes one record per lane");
+// Geometry of a cloud's team: CS CTAs x WPC warps = 32 warps (one record per lane of the reducing warp).
+//   Geo<8, 4>  : the latency mapping described above (8 SMs per cloud, one warp per scheduler)
+//   Geo<1, 32> : the same algorithm inside ONE CTA of 32 warps (one SM per cloud, st.async to itself + mbarrier instead of a
+//                __syncthreads per pick, tiles in L2).  Bit-exact, measured 6.4 ms per 65 536-point cloud against 4.8 ms for
+//                grid.cu's fps_grid_kernel, which therefore stays the throughput mapping; kept behind DPM_FPS_ONESM=1.
+template <int CS_, int WPC_>
+struct Geo {
+    static constexpr int CS = CS_, WPC = WPC_, T = WPC_ * 32, NW = CS_ * WPC_;
+    static_assert(NW == 32, "the record reduce takes one record per lane");
+};
+constexpr int FC_NW = 32;                 // warps per cloud = records per pick
 constexpr unsigned FC_TX = FC_NW * 32u;   // bytes that complete one pick's mbarrier phase
 
-struct __align__(16) FcShared {
-    uint4 rec[2][FC_NW][2];     // [parity][warp of the cluster]: {value bits, ~index, x, y}, {z, second value of the warp, -, -}
-    uint4 stage[2][FC_WPC][2];  // [parity][warp]: this warp's record, written by its winning lane, pushed out by 16 lanes
-    uint4 win[2][FC_WPC][3];    // [parity][warp]: the round's result as this warp reduced it: winner {~index, x, y, z},
-                                //   {second value of the winner's warp}, runner-up {~index, x, y, z}
-    uint4 tmp[2][FC_WPC];       // [toggle][warp]: broadcast slot of the bucket-level arg-max
+template <int WPC>
+struct __align__(16) FcSharedT {
+    uint4 rec[2][FC_NW][2];   // [parity][warp of the team]: {value bits, ~index, x, y}, {z, second value of the warp, -, -}
+    uint4 stage[2][WPC][2];   // [parity][warp]: this warp's record, written by its winning lane, pushed out by 2 CS lanes
+    uint4 win[2][WPC][3];     // [parity][warp]: the round's result as this warp reduced it: winner {~index, x, y, z},
+                              //   {second value of the winner's warp}, runner-up {~index, x, y, z}
+    uint4 tmp[2][WPC];        // [toggle][warp]: broadcast slot of the bucket-level arg-max
     unsigned long long bar[2];
 };
 
@@ -101,7 +108,8 @@ __device__ __forceinline__ void fc_st_async16(unsigned raddr, uint4 v, unsigned 
                  : "memory");
 }
 
-__device__ __forceinline__ void fc_setup(FcShared &sh, int tid) {
+template <typename SH>
+__device__ __forceinline__ void fc_setup(SH &sh, int tid) {
     if (tid == 0) {
         fc_mbar_init(fc_s32(&sh.bar[0]), 1);
         fc_mbar_init(fc_s32(&sh.bar[1]), 1);
@@ -167,7 +175,8 @@ __device__ __forceinline__ void fc_bucket(uint4 *slot, const FcCand &c, bool own
 
 // This warp's record of round r: the winning lane writes it, 16 lanes push it into the record table of every CTA of
 // the cluster (ra / rb: this lane's remote record / mbarrier address for the parity of r).
-__device__ __forceinline__ void fc_publish(FcShared &sh, int r, int warp, int lane, unsigned ra, unsigned rb, const FcCand &c) {
+template <int CS, typename SH>
+__device__ __forceinline__ void fc_publish(SH &sh, int r, int warp, int lane, unsigned ra, unsigned rb, const FcCand &c) {
     uint4 *st = sh.stage[r & 1][warp];
     const unsigned vmax = __reduce_max_sync(0xffffffffu, c.b);
     const bool eq = c.b == vmax;
@@ -187,7 +196,7 @@ __device__ __forceinline__ void fc_publish(FcShared &sh, int r, int warp, int la
         }
         __syncwarp();
     }
-    if (lane < 2 * FC_CS) {
+    if (lane < 2 * CS) {
         uint4 q = st[lane & 1];
         if (lane & 1) q.y = v2;
         fc_st_async16(ra, q, rb);
@@ -200,7 +209,8 @@ struct FcPick {
     bool two;
 };
 // wait for the 32 records of round r and reduce them: the same result in every warp of the cluster
-__device__ __forceinline__ void fc_collect(FcShared &sh, int r, int warp, int lane, bool armer, bool allow_two, FcPick &o) {
+template <typename SH>
+__device__ __forceinline__ void fc_collect(SH &sh, int r, int warp, int lane, bool armer, bool allow_two, FcPick &o) {
     const int par = r & 1;
     const unsigned parity = (unsigned)(((r - 1) >> 1) & 1);
     const unsigned bar = fc_s32(&sh.bar[par]);
@@ -237,8 +247,9 @@ __device__ __forceinline__ void fc_collect(FcShared &sh, int r, int warp, int la
     o.two = two;
 }
 // this lane's remote addresses (lanes < 16: destination CTA lane / 2, record half lane & 1) for both parities
-__device__ __forceinline__ void fc_remote(FcShared &sh, int gw, int lane, unsigned (&ra)[2], unsigned (&rb)[2]) {
-    const unsigned dest = ((unsigned)lane >> 1) & (FC_CS - 1), half = (unsigned)lane & 1u;
+template <int CS, typename SH>
+__device__ __forceinline__ void fc_remote(SH &sh, int gw, int lane, unsigned (&ra)[2], unsigned (&rb)[2]) {
+    const unsigned dest = ((unsigned)lane >> 1) & (CS - 1), half = (unsigned)lane & 1u;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         ra[p] = fc_mapa(fc_s32(&sh.rec[p][gw][half]), dest);
@@ -259,20 +270,22 @@ __device__ __forceinline__ void fc_emit(size_t o, unsigned sel, float x, float y
     if (lane == 3 && new_pad) new_pad[o] = 0;
 }
 
-template <int PPL, bool RES>
-__global__ void __launch_bounds__(FC_T, 1)
+template <int PPL, bool RES, typename G>
+__global__ void __launch_bounds__(G::T, 1)
 fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
                         const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
                         int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
                         uint8_t *__restrict__ new_pad, int *__restrict__ new_len32) {
     constexpr int BS = 32 * PPL, D = PPL <= 2 ? 2 : 1;
+    constexpr int FC_CS = G::CS, FC_WPC = G::WPC, FC_T = G::T;
+    using FcShared = FcSharedT<G::WPC>;
     extern __shared__ __align__(16) unsigned char fc_smem[];
     FcShared &sh = *reinterpret_cast<FcShared *>(fc_smem);
     float4 *spts = reinterpret_cast<float4 *>(fc_smem + sizeof(FcShared));  // [FC_WPC * 32 * BS]
     float *smin = reinterpret_cast<float *>(spts + (RES ? FC_WPC * 32 * BS : 0));
 
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned rank = fc_rank();
+    const unsigned rank = FC_CS > 1 ? fc_rank() : 0u;
     const int gw = (int)rank * FC_WPC + warp;
     const int len = desc[b].nvalid;
     const int kn = min(len, K);
@@ -283,7 +296,7 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
     const float INF = __int_as_float(0x7f800000);
     fc_setup(sh, tid);
     unsigned ra[2], rb[2];
-    fc_remote(sh, gw, lane, ra, rb);
+    fc_remote<FC_CS>(sh, gw, lane, ra, rb);
     int tog = 0;
 
     // ---- prologue: tiles -> shared memory, bucket boxes, min-distances = +inf (sentinels 0) ----
@@ -336,7 +349,8 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
         s1x = p0.x; s1y = p0.y; s1z = p0.z;
     }
     if (gw == 0 && kn > 0) fc_emit(ob, 0u, s1x, s1y, s1z, lane, idx64, idx32, new_xyz4, new_pad);
-    fc_cluster_sync();  // every CTA's mbarriers are initialised and armed before the first record arrives
+    if (FC_CS > 1) fc_cluster_sync();  // every CTA's mbarriers are initialised and armed before the first record arrives
+    else __syncthreads();
 
 #ifdef DPM_FC_PROFILE
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
@@ -418,7 +432,7 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
             }
         }
         FC_TICK(1);
-        fc_publish(sh, r, warp, lane, (r & 1) ? ra[1] : ra[0], (r & 1) ? rb[1] : rb[0], c);
+        fc_publish<FC_CS>(sh, r, warp, lane, (r & 1) ? ra[1] : ra[0], (r & 1) ? rb[1] : rb[0], c);
         FC_TICK(3);
         // ---- phase B, in the shadow of the exchange: the touched buckets' new maxima, for their owners ----
         if (RES) {
@@ -472,18 +486,19 @@ fps_grid_cluster_kernel(const float4 *__restrict__ sorted, float *__restrict__ m
         }
         if (tid == 0 && new_len32) new_len32[b] = kn;
     }
-    fc_cluster_sync();  // no CTA may exit while a peer can still store into its shared memory
+    if (FC_CS > 1) fc_cluster_sync();  // no CTA may exit while a peer can still store into its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // small clouds: P points per thread in registers, point i = j * 1024 + (warp of the cluster) * 32 + lane
 // ---------------------------------------------------------------------------------------------------------
 template <int P>
-__global__ void __launch_bounds__(FC_T, 1)
+__global__ void __launch_bounds__(Geo<8, 4>::T, 1)
 fps_brute_cluster_kernel(const float4 *__restrict__ xyz4, int N, const int *__restrict__ len32, int K,
                          int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
                          uint8_t *__restrict__ new_pad, int *__restrict__ new_len32) {
-    __shared__ FcShared sh;
+    constexpr int FC_CS = 8, FC_WPC = 4, FC_T = 128;
+    __shared__ FcSharedT<4> sh;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned rank = fc_rank();
     const int gw = (int)rank * FC_WPC + warp;
@@ -493,7 +508,7 @@ fps_brute_cluster_kernel(const float4 *__restrict__ xyz4, int N, const int *__re
     const size_t ob = (size_t)b * K;
     fc_setup(sh, tid);
     unsigned ra[2], rb[2];
-    fc_remote(sh, gw, lane, ra, rb);
+    fc_remote<FC_CS>(sh, gw, lane, ra, rb);
 
     float x[P], y[P], z[P], m[P];
 #pragma unroll
@@ -527,7 +542,7 @@ fps_brute_cluster_kernel(const float4 *__restrict__ xyz4, int N, const int *__re
             // m >= 0: the bit pattern is order preserving; tie key = ~index (never 0: index < 2^31)
             fc_merge(c, __float_as_uint(m[j]), 0xffffffffu - (unsigned)(j * (FC_NW * 32) + gw * 32 + lane), x[j], y[j], z[j]);
         }
-        fc_publish(sh, r, warp, lane, (r & 1) ? ra[1] : ra[0], (r & 1) ? rb[1] : rb[0], c);
+        fc_publish<FC_CS>(sh, r, warp, lane, (r & 1) ? ra[1] : ra[0], (r & 1) ? rb[1] : rb[0], c);
         FcPick o;
         fc_collect(sh, r, warp, lane, tid == 0, k + 1 < kn, o);
         if (gw == 0) {
@@ -556,8 +571,13 @@ fps_brute_cluster_kernel(const float4 *__restrict__ xyz4, int N, const int *__re
 // ---------------------------------------------------------------------------------------------------------
 static std::atomic<int> g_fps_mode{0};  // 0 auto, 1 one CTA per cloud, 2 cluster per cloud
 
+using GeoCluster = Geo<8, 4>;   // latency mapping
+using GeoOneSm = Geo<1, 32>;    // throughput mapping
+constexpr int FC_CS = GeoCluster::CS, FC_T = GeoCluster::T;
+
+template <typename G>
 static size_t fc_grid_smem(int ppl, bool res) {
-    return sizeof(FcShared) + (res ? (size_t)FC_WPC * 32 * 32 * ppl * (sizeof(float4) + sizeof(float)) : 0);
+    return sizeof(FcSharedT<G::WPC>) + (res ? (size_t)G::WPC * 32 * 32 * ppl * (sizeof(float4) + sizeof(float)) : 0);
 }
 
 // clouds whose clusters are co-resident: what the hardware can place of the largest cluster kernel (8 CTAs x 166 KB
@@ -567,8 +587,8 @@ int fps_cluster_capacity() {
     const int dev = current_device() & 63;
     if (cached[dev] == 0) {
         int n = 0;
-        auto kern = fps_grid_cluster_kernel<2, true>;
-        const size_t smem = fc_grid_smem(2, true);
+        auto kern = fps_grid_cluster_kernel<2, true, GeoCluster>;
+        const size_t smem = fc_grid_smem<GeoCluster>(2, true);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(FC_CS, 64, 1);
         cfg.blockDim = dim3(FC_T, 1, 1);
@@ -616,38 +636,38 @@ bool fps_cluster_mode_small(int B) {
     return B <= (maxb > fps_cluster_capacity() ? maxb : fps_cluster_capacity());
 }
 
-template <typename Kern, typename... Args>
+template <typename G, typename Kern, typename... Args>
 static int fc_launch(Kern kern, size_t smem, int B, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(FC_CS, B, 1);
-    cfg.blockDim = dim3(FC_T, 1, 1);
+    cfg.gridDim = dim3(G::CS, B, 1);
+    cfg.blockDim = dim3(G::T, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = FC_CS;
+    attr[0].val.clusterDim.x = G::CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1;   // also for one CTA per cloud: the records travel by st.async to shared::cluster addresses
     DPM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
     count_launch("fps", st);
     return DPM_OK;
 }
 
-template <int PPL, bool RES>
+template <int PPL, bool RES, typename G>
 static int fps_grid_cluster_t(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                               float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
-    auto kern = fps_grid_cluster_kernel<PPL, RES>;
-    const size_t smem = fc_grid_smem(PPL, RES);
+    auto kern = fps_grid_cluster_kernel<PPL, RES, G>;
+    const size_t smem = fc_grid_smem<G>(PPL, RES);
     static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
     const unsigned long long devbit = 1ull << (current_device() & 63);
     if (!(configured & devbit)) {
         DPM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured |= devbit;
     }
-    return fc_launch(kern, smem, B, st, (const float4 *)g.sorted, g.mind, g.npad, (const GridDesc *)g.desc, xyz4, N, K, idx64,
-                     idx32, new_xyz4, new_pad, new_len32);
+    return fc_launch<G>(kern, smem, B, st, (const float4 *)g.sorted, g.mind, g.npad, (const GridDesc *)g.desc, xyz4, N, K, idx64,
+                        idx32, new_xyz4, new_pad, new_len32);
 }
 
 int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
@@ -655,12 +675,26 @@ int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, i
     if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
     prof_note(N, K);
     switch (grid_ppl(N)) {
-        case 1: return fps_grid_cluster_t<1, true>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
-        case 2: return fps_grid_cluster_t<2, true>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
-        case 4: return fps_grid_cluster_t<4, false>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
-        case 8: return fps_grid_cluster_t<8, false>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 1: return fps_grid_cluster_t<1, true, GeoCluster>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 2: return fps_grid_cluster_t<2, true, GeoCluster>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 4: return fps_grid_cluster_t<4, false, GeoCluster>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 8: return fps_grid_cluster_t<8, false, GeoCluster>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
     }
     return fail(DPM_ERR_UNSUPPORTED, "fps: no cluster kernel for N=%d", N);
+}
+
+// the same algorithm with one CTA (one SM) per cloud, tiles in L2: the throughput mapping
+int fps_grid_onesm_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
+                          float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
+    if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
+    prof_note(N, K);
+    switch (grid_ppl(N)) {
+        case 1: return fps_grid_cluster_t<1, false, GeoOneSm>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 2: return fps_grid_cluster_t<2, false, GeoOneSm>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 4: return fps_grid_cluster_t<4, false, GeoOneSm>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+        case 8: return fps_grid_cluster_t<8, false, GeoOneSm>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+    }
+    return fail(DPM_ERR_UNSUPPORTED, "fps: no kernel for N=%d", N);
 }
 
 int fps_brute_cluster_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64, int32_t *idx32,
@@ -668,8 +702,8 @@ int fps_brute_cluster_launch(const float4 *xyz4, int B, int N, const int *len32,
     prof_note(N, K);
 #define DPM_FB_CASE(p)                                                                                              \
     if (N <= p * FC_NW * 32)                                                                                        \
-        return fc_launch(fps_brute_cluster_kernel<p>, 0, B, st, xyz4, N, len32, K, idx64, idx32, new_xyz4, new_pad, \
-                         new_len32);
+        return fc_launch<GeoCluster>(fps_brute_cluster_kernel<p>, 0, B, st, xyz4, N, len32, K, idx64, idx32, new_xyz4, new_pad, \
+                                     new_len32);
     DPM_FB_CASE(1) DPM_FB_CASE(2) DPM_FB_CASE(4) DPM_FB_CASE(8)
 #undef DPM_FB_CASE
     return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the register-resident cluster limit %d", N, FPS_BRUTE_CLUSTER_MAX_N);

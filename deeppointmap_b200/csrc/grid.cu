@@ -16,6 +16,8 @@
 //
 // The within-cell order of the sorted array depends on atomic arrival order; every result is
 // made independent of it by explicit (value, original index) comparisons.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dpm {
@@ -430,6 +432,13 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
     if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
     if (fps_cluster_mode(B))  // few clouds: 8 SMs per cloud instead of one (fps_cluster.cu)
         return fps_grid_cluster_launch(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+    // Measured and rejected (round 2): the cluster kernel's algorithm (broadcast arg-max, two picks per round, mbarrier
+    // record exchange) in a ONE-CTA geometry of 32 warps, fps_grid_onesm_launch: bit-exact, but 6.4 ms against this
+    // kernel's 4.8 ms per 65 536-point cloud -- with 8 warps per scheduler the exchange through st.async + mbarrier
+    // costs more than one __syncthreads, and the bucket maxima sit on the critical path when the tiles are not in
+    // shared memory.  DPM_FPS_ONESM=1 selects it for A/B runs.
+    static const bool onesm_new = getenv("DPM_FPS_ONESM") && atoi(getenv("DPM_FPS_ONESM")) == 1;
+    if (onesm_new) return fps_grid_onesm_launch(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
     const int ppl = grid_ppl(N);
     prof_note(N, K);
 #define DPM_FG_ARGS g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, new_pad, new_len32
