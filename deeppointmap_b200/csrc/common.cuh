@@ -185,7 +185,7 @@ bool linear_ln_tc_launch(const float *X, int ldx, const float *W, int ldw, const
 // the scratch buffer `tmp` (M x N, may be Y itself when Y does not alias res / post)
 int linear_ln_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res, int ldres,
                      const float *gamma, const float *beta, const float *post, int ldpost, float *tmp, float *Y, int ldy,
-                     int M, int N, int K, int act, cudaStream_t st);
+                     int M, int N, int K, int act, cudaStream_t st, int tmp_copies = 1);
 int layernorm_launch(const float *X, int ldx, const float *gamma, const float *beta, const float *post, int ldpost,
                      float *Y, int ldy, int M, int C, int act, cudaStream_t st);
 int group_launch(const float *Z, const float4 *xyz4, const float4 *ctr4, const int32_t *gidx, const float *Wxyz,

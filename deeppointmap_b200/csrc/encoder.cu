@@ -329,7 +329,8 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
             float *Z2 = a.get<float>((size_t)B * S * Cout);
             float *la = a.get<float>((size_t)B * S * Cout);
             float *h1 = a.get<float>((size_t)B * S * Ch);
-            float *h2 = a.get<float>((size_t)B * S * Cout);
+            const int h2_copies = (Ch >= 1024 && Cout > 256) ? 4 : 1;  // split-K partials of the unfused deep layer
+            float *h2 = a.get<float>((size_t)B * S * Cout * h2_copies);
             float *nf = a.get<float>((size_t)B * S * Cout);
             const float *Wla = W(), *bla = W(), *gla = W(), *bela = W();
             const float *W1 = W(), *b1 = W(), *g1 = W(), *be1 = W();
@@ -356,7 +357,7 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
                 DPM_TRY(linear_ln_launch(la, Cout, W1, Cout, b1, nullptr, 0, g1, be1, nullptr, 0, h1, h1, Ch, B * S, Ch, Cout,
                                          DPM_ACT_RELU, st));
                 DPM_TRY(linear_ln_launch(h1, Ch, W2, Ch, b2, nullptr, 0, g2w, be2, dst.fea, Cout, h2, nf, Cout, B * S, Cout, Ch,
-                                         DPM_ACT_RELU, st));
+                                         DPM_ACT_RELU, st, h2_copies));
             }
             knn_off += (size_t)B * S * K;
             dst.fea = nf;

@@ -98,3 +98,49 @@ def test_registry_branches_on_b200_ops(t3d):
     # knn_gather
     g = t3d.knn_gather(pts.to(dev), res.idx)
     assert torch.equal(g.cpu(), pts[torch.arange(B)[:, None, None], wi])
+
+
+@pytest.mark.gpu
+def test_reference_encoder_on_b200_ops_matches_dropin_encoder():
+    """Seam #2 for real: the REFERENCE's own Encoder (its pointnext.py / utils.py, unmodified) on the GPU,
+    with `pytorch3d.ops` resolving to libdpm_b200.so -- its Sampler / Querier registry picks the `-t3d` branches -- against
+    the drop-in Encoder on the same frame.  Same index contract on both sides, so the descriptors agree to 1e-4."""
+    from oracle import ref_loader
+    if ref_loader.ref_root() is None or ref_loader.checkpoint_path() is None:
+        pytest.skip("reference sources not on this box (oracle/_ref/reference is made by build())")
+    import numpy as np
+    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("pytorch3d", "network")}
+    try:
+        for k in saved_mods:
+            sys.modules.pop(k, None)
+        renc, rdec, rcfg = ref_loader.load_models("cuda:0", ops="b200")
+        import network.encoder.utils as RU
+        assert RU.knn_points.__module__ == "deeppointmap_b200.ops"           # the seam is live, no pure-torch fallback
+        assert type(renc).__module__ == "network.encoder.encoder"
+        from deeppointmap_b200 import Encoder
+        from oracle import model_ref as M
+        cfg = M.default_config()
+        ck = torch.load(ref_loader.checkpoint_path(), map_location="cpu")
+        ours = Encoder(cfg).eval()
+        ours.load_state_dict(ck["encoder"], strict=True)
+        ours = ours.to("cuda:0")
+        g = np.load(os.path.join(ROOT, "tests", "golden", "sample_pair.npz"))
+        pts = torch.from_numpy(g["cloud0"])[None].to("cuda:0")
+        pad = torch.zeros(1, pts.shape[2], dtype=torch.bool, device="cuda:0")
+        # the reference's 1x1 convolutions go through cuDNN, whose default on this GPU is TF32 (1e-3 relative):
+        # switch it off so that the reference itself computes in fp32
+        tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                rc, rf, rp = renc(pts, pad)
+                oc, of, op = ours(pts, pad)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        assert torch.equal(rc, oc) and torch.equal(rp, op)                    # same FPS picks, bit for bit
+        assert float((rf - of).abs().max() / rf.abs().max()) < 1e-4
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k.split(".")[0] in ("pytorch3d", "network")]:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved_mods)
