@@ -18,6 +18,10 @@
 //              of P V); a ring of two K stages and one of two V stages.
 //   warp 12    one lane issues the MMAs: S(i+2) is in flight while the softmax warps work on tile i and P V (i)
 //              runs as soon as P(i) is in shared memory; completion goes through tcgen05.commit -> mbarriers.
+// Measured and rejected: 16 softmax warps (4 per TMEM lane quarter, 16 keys each) instead of 8 -- 0.359 against 0.335 ms
+// at 4096 x 4096: the max / exp phase does not shrink (1 315 cycles per tile), because all softmax warps wait for the same
+// S tile and then hit the special-function unit together (8 448 ex2 per tile at 16 per clock = 530 cycles) behind a wider
+// barrier.  What would help is two query tiles per CTA in ping-pong (one group's exp under the other's MMAs).
 // P never touches shared memory: the softmax warps write it back into TENSOR MEMORY over the scores it came from
 // (tcgen05.st) and P V takes its A operand from there -- a first version that staged P in shared memory (64 KB per
 // tile written, 64 KB read by the MMAs) was bound by the shared-memory pipe: 3 400 cycles per tile, none of them
