@@ -123,13 +123,21 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define TC_STAMP(i) do { } while (0)
 #endif
 
+// the two warps that share a TMEM lane quarter (immediate barrier ids: a register id makes ptxas reserve all 16)
+__device__ __forceinline__ void pair_barrier(int quarter) {
+    if (quarter == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+    else if (quarter == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+    else if (quarter == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+    else asm volatile("bar.sync 4, 64;" ::: "memory");
+}
+
 struct LnArgs {  // fused LayerNorm epilogue: Y = act(LN_N(acc + bias + res) * gamma + beta + post)
     const float *gamma, *beta, *post;
     int ldpost;
 };
 
-template <int BN, int STAGES, bool PRESPLIT, bool LN>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN, int STAGES, bool PRESPLIT, bool LN, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
 linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ W, int ldw,
                  const float *__restrict__ bias, const float *res, int ldres, float *Y,
                  int ldy, int M, int N, int K, int act, long long sX, long long sW, long long sY, long long wlo_off,
@@ -269,7 +277,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
                 sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 4);
                 if ((lane & 7) == 0) stat[grp * 128 + quarter * 32 + i * 4 + rsub] = sum[i];
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // the two warps of this lane quarter
+            pair_barrier(quarter);  // the two warps of this lane quarter
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int lr = quarter * 32 + i * 4 + rsub;
@@ -297,7 +305,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
                 sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 4);
                 if ((lane & 7) == 0) stat[256 + grp * 128 + quarter * 32 + i * 4 + rsub] = sum[i];
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            pair_barrier(quarter);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int lr = quarter * 32 + i * 4 + rsub;
@@ -412,12 +420,46 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
     if (tid == 0) TC_STAMP(5);
 }
 
+template <int BN, int STAGES, bool PRESPLIT, bool LN, int MINB>
+static int launch_s(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
+                    const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
+                    int act, long long wlo_off, cudaStream_t st, LnArgs ln);
+
+// SHALLOW contractions (K <= 64 / 128: the early encoder stages, 1024 row tiles per launch): the default stage count
+// would hold 160-200 KB of shared memory for a K loop of 1-4 blocks and pin one CTA per SM, whose 2.8 us fill and
+// 5-6 us epilogue then run with the tensor core idle.  With as many stages as K blocks (<= 2) two CTAs share an SM
+// (<= 113 KB, <= 256 TMEM columns each) and one's epilogue overlaps the other's loads.
 template <int BN, int STAGES, bool PRESPLIT, bool LN = false>
 static int launch_t(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
                     const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
                     int act, long long wlo_off, cudaStream_t st, LnArgs ln = LnArgs{nullptr, nullptr, nullptr, 0}) {
-    auto kern = linear_tc_kernel<BN, STAGES, PRESPLIT, LN>;
-    const size_t smem = (size_t)STAGES * (2 * A_TILE + 2 * BN * 128) + 1024;
+    static const bool shallow_off = getenv("DPM_TC_NO_SHALLOW") != nullptr;
+    const int nkb = (K + BK - 1) / BK, mt = (M + BM - 1) / BM;
+    if constexpr (PRESPLIT && BN <= 128) {
+        if (!shallow_off && mt > 148) {
+            if constexpr (BN <= 64) {
+                if (nkb <= 8 && nkb >= 2)
+                    return launch_s<BN, 2, PRESPLIT, LN, 2>(X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act,
+                                                            wlo_off, st, ln);
+            }
+            if (nkb == 1)
+                return launch_s<BN, 1, PRESPLIT, LN, 2>(X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act,
+                                                        wlo_off, st, ln);
+        }
+    }
+    return launch_s<BN, STAGES, PRESPLIT, LN, 1>(X, ldx, sX, W, ldw, sW, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, wlo_off,
+                                                 st, ln);
+}
+
+template <int BN, int STAGES, bool PRESPLIT, bool LN, int MINB>
+static int launch_s(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
+                    const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
+                    int act, long long wlo_off, cudaStream_t st, LnArgs ln) {
+    auto kern = linear_tc_kernel<BN, STAGES, PRESPLIT, LN, MINB>;
+    // the pipeline stages double as the epilogue's staging area: LayerNorm parks the whole 128 x (BN + 4) tile + statistics
+    constexpr size_t stage_bytes = (size_t)STAGES * (2 * A_TILE + 2 * BN * 128);
+    constexpr size_t epi_bytes = LN ? (size_t)(128 * (BN + 4) + 4 * 128) * 4 : (size_t)8 * 32 * 36 * 4;
+    const size_t smem = stage_bytes > epi_bytes ? stage_bytes : epi_bytes;
     static thread_local unsigned long long configured = 0ull;  // one bit per device: function attributes are per context
     const unsigned long long devbit = 1ull << (current_device() & 63);
     if (!(configured & devbit)) {
