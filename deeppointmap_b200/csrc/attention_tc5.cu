@@ -22,6 +22,10 @@
 // at 4096 x 4096: the max / exp phase does not shrink (1 315 cycles per tile), because all softmax warps wait for the same
 // S tile and then hit the special-function unit together (8 448 ex2 per tile at 16 per clock = 530 cycles) behind a wider
 // barrier.  What would help is two query tiles per CTA in ping-pong (one group's exp under the other's MMAs).
+// Also measured and rejected: the 8 softmax warps as two ping-pong groups over even / odd key tiles (thread = whole row of 64
+// keys, own running max / sum / output per group, merged at the end, four O buffers): bit-for-bit fine, 0.350 ms -- the
+// groups then wait ~1 400 cycles per tile for S(i+2), which cannot be issued before P V (i) because it overwrites P(i)
+// in tensor memory, and the 512 TMEM columns are all in use (S / P 2 x 128, O 4 x 64).
 // P never touches shared memory: the softmax warps write it back into TENSOR MEMORY over the scores it came from
 // (tcgen05.st) and P V takes its A operand from there -- a first version that staged P in shared memory (64 KB per
 // tile written, 64 KB read by the MMAs) was bound by the shared-memory pipe: 3 400 cycles per tile, none of them
