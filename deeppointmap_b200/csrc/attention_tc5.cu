@@ -175,11 +175,12 @@ attention_tc5_kernel(const float *__restrict__ Q, int ldq, const float *__restri
             AT5_TICK(1);
             float s[32];
             {
-                float x[32];
-                tmem_ld32(tl + TM_S + 128u * b + (unsigned)col0, s);
-                tmem_ld32(tl + TM_S + 128u * b + 64u + (unsigned)col0, x);
+                unsigned rh[32], rx[32];  // both loads in flight, one wait
+                tmem_ld32_nowait(tl + TM_S + 128u * b + (unsigned)col0, rh);
+                tmem_ld32_nowait(tl + TM_S + 128u * b + 64u + (unsigned)col0, rx);
+                tmem_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 32; ++c) s[c] += x[c];
+                for (int c = 0; c < 32; ++c) s[c] = __uint_as_float(rh[c]) + __uint_as_float(rx[c]);
             }
             AT5_TICK(2);
             const int nvalid = Lk - i * BKEY - col0;  // keys of my half that exist
@@ -194,22 +195,28 @@ attention_tc5_kernel(const float *__restrict__ Q, int ldq, const float *__restri
                 for (int c = 0; c < 32; ++c)
                     if (kd[c]) s[c] = NEG;
             }
-            float mx = NEG;
+            float mx4[4] = {NEG, NEG, NEG, NEG};  // four independent chains instead of one of 32 dependent fmax
 #pragma unroll
-            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, s[c]);
+            for (int c = 0; c < 32; c += 4) {
+                mx4[0] = fmaxf(mx4[0], s[c]); mx4[1] = fmaxf(mx4[1], s[c + 1]);
+                mx4[2] = fmaxf(mx4[2], s[c + 2]); mx4[3] = fmaxf(mx4[3], s[c + 3]);
+            }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             xm[b][wg][row] = mx;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // the two warps that share these rows
             // (slot b is rewritten two tiles later, i.e. after another barrier that the partner only reaches once it has read it)
             float m_new = fmaxf(m_run, fmaxf(mx, xm[b][wg ^ 1][row]));
             if (m_new == NEG) m_new = 0.f;  // every key so far masked: keep the exponents finite
             const float corr = ex2(m_run - m_new);
-            float lsum = 0.f;
+            float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                s[c] = ex2(s[c] - m_new);
-                lsum += s[c];
+            for (int c = 0; c < 32; c += 4) {
+                s[c] = ex2(s[c] - m_new);         ls4[0] += s[c];
+                s[c + 1] = ex2(s[c + 1] - m_new); ls4[1] += s[c + 1];
+                s[c + 2] = ex2(s[c + 2] - m_new); ls4[2] += s[c + 2];
+                s[c + 3] = ex2(s[c + 3] - m_new); ls4[3] += s[c + 3];
             }
-            l_run = fmaf(l_run, corr, lsum);
+            l_run = fmaf(l_run, corr, (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
             m_run = m_new;
             AT5_TICK(3);
             // P (my 32 keys) -> the A operand of P V, IN TENSOR MEMORY and in place of the scores it was computed from:
