@@ -174,12 +174,14 @@ def information_matrix(pointcloud_1: torch.Tensor, pointcloud_2: torch.Tensor, S
 
 
 def preprocess_frame(raw: torch.Tensor, voxel_size: float = 0.3, min_dis: float = 1.0, max_dis: float = 60.0,
-                     ratio: float = 60.0, max_voxels: int = 1 << 26, outlier=None, lowpass=None) -> torch.Tensor:
+                     ratio: float = 60.0, max_voxels: int = 1 << 25, outlier=None, lowpass=None) -> torch.Tensor:
     """Raw frame -> encoder input on the device: BinReader's NaN-row drop, VoxelSample(voxel_size, 'first'),
     DistanceSample(min_dis, max_dis), [OutlierFilter(*outlier), e.g. outlier=(10, 3.0) as in the shipped YAML],
     CoordinatesNormalization(ratio) (dataloader/heads/bin.py:16-17, dataloader/transforms.py:230-246, 331-356,
     387-407).  raw (N, C>=3) CUDA fp32 rows (a KITTI .bin is (N,4)) -> (3, n) fp32, points in the reference's
-    order (ascending voxel id).  One host sync per data-dependent size."""
+    order (ascending voxel id).  One host sync per data-dependent size.  max_voxels bounds the dense first-index table
+    (4 bytes per cell of the frame's bounding grid, 134 MB of scratch at the default: a 160 x 160 x 30 m frame at 0.3 m
+    has 28 M cells); a frame whose grid is larger raises and asks for a higher bound."""
     if outlier is not None or lowpass is not None:
         # the whole shipped YAML chain on the device: VoxelSample -> DistanceSample -> [OutlierFilter(*outlier)] ->
         # [LowPassFilter(*lowpass), e.g. lowpass=(0.5, 16, 2.0, 4)] -> CoordinatesNormalization

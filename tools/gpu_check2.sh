@@ -13,7 +13,7 @@ python -c "import os; print('cpus', os.cpu_count())" >> gpurun_out/${TAG}_smi.tx
 ( timeout 600 python bench.py --impl reference --gpus 1 --steps 5 --warmup 1 2>/dev/null | tail -1 ) > gpurun_out/${TAG}_bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --streams 1 --no-cpu-baseline --no-e2e --no-batch1 --no-extra > gpurun_out/${TAG}_ncu_bench.log 2>&1
-bash tools/gpu_ncu.sh ${TAG} 32 'fps_grid_kernel<.int.2' 'knn_grid_kernel' 'linear_tc_kernel<.int.256, .int.2, .bool.1, .bool.0' \
+bash tools/gpu_ncu.sh ${TAG} 32 'fps_grid_kernel<.int.2' 'knn_grid_kernel' 'linear_tc_kernel<.int.256, .int.2, .bool.1, .bool.0' 'linear_tc_kernel<.int.128, .int.1, .bool.1, .bool.1' \
     'linear_tc_kernel<.int.256, .int.2, .bool.1, .bool.1' 'attention_tc5_kernel' 'group_lane_kernel<.int.32, .bool.0' 'pair_select_kernel'
 bash tools/gpu_ncu.sh ${TAG}b1 1 'fps_grid_cluster_kernel<.int.2'
 cat gpurun_out/${TAG}_pytest.log gpurun_out/${TAG}_smoke.log
