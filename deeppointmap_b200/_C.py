@@ -4,6 +4,7 @@ There is no fallback: if the library is missing or the tensors are not on a CUDA
 calls raise.  Build it with `python -m deeppointmap_b200.build` (nvcc, sm_100a).
 """
 import ctypes
+import itertools
 import os
 import threading
 
@@ -44,6 +45,7 @@ _SIGS = {
     "dpm_launch_count_reset": ([], None),
     "dpm_prof_begin": ([_vp], _i),
     "dpm_prof_end": ([ctypes.c_char_p, _sz], _i),
+    "dpm_set_weights_epoch": ([ctypes.c_ulonglong], None),
     "dpm_fps_f32": ([_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp], _i),
     "dpm_fps_workspace_bytes": ([_i, _i, _i, _i], _sz),
     "dpm_set_fps_mode": ([_i], None),
@@ -133,6 +135,30 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+_buffer_ids = itertools.count(1)
+_epoch_ids = itertools.count(1)
+_epochs = {}
+
+
+REUSE_SPLIT = not os.environ.get("DPM_NO_SPLIT_REUSE")
+
+
+def weights_epoch(fingerprint, ws: torch.Tensor) -> int:
+    """A non-zero token that changes whenever the weights' fingerprint or the scratch buffer's identity does (see
+    dpm_set_weights_epoch): lets a call skip re-splitting weights it already split into this very buffer."""
+    key = (fingerprint, getattr(ws, "_dpm_id", 0))
+    # never while a CUDA graph is being captured: a replay must re-split (it is the only way an in-place weight update
+    # can reach a captured call)
+    if key[1] == 0 or not REUSE_SPLIT or torch.cuda.is_current_stream_capturing():
+        return 0
+    e = _epochs.get(key)
+    if e is None:
+        if len(_epochs) > 256:
+            _epochs.clear()
+        e = _epochs[key] = next(_epoch_ids)
+    return e
+
+
 class _Workspaces(threading.local):
     """One growable scratch buffer per (host thread, device, slot); a slot is "<module><stream handle>", so calls on
     different streams never share scratch.  At most MAX_SLOTS buffers are kept per thread (least recently used goes
@@ -150,6 +176,7 @@ class _Workspaces(threading.local):
         if b is None or b.numel() < nbytes:
             b = torch.empty(int(nbytes) + (int(nbytes) >> 4) + 4096, dtype=torch.uint8, device=device)
             b.record_stream(torch.cuda.current_stream(device))
+            b._dpm_id = next(_buffer_ids)   # identity of THIS allocation (an address can be reused by a later one)
         self.buf[key] = b
         while len(self.buf) > self.MAX_SLOTS:
             self.buf.pop(next(iter(self.buf)))

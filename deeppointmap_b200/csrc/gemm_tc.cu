@@ -605,8 +605,44 @@ void split_add(Arena &a, const float *W, int rows, int cols, int ld) {
     j.src = W; j.dst = dst; j.rows = rows; j.cols = cols; j.ld = ld; j.pad = (cols + 31) & ~31;
 }
 
+// ---- optional reuse of the split copies across calls ---------------------------------------------------
+// By default every call re-splits its weights (nothing derived from the weights outlives a call).  A caller that KNOWS
+// its weights and its workspace are unchanged since its previous call can say so with dpm_set_weights_epoch(e != 0): the
+// split launch is then skipped when the same epoch last wrote the same jobs (same sources, shapes, destinations).  The
+// epoch must change whenever a weight tensor or the workspace buffer does (deeppointmap_b200 derives it from the
+// parameters' version counters and the scratch buffer's identity); 0 switches the reuse off again.
+static thread_local unsigned long long g_epoch = 0ull;
+struct SplitSeen {
+    unsigned long long epoch, hash;
+    const float *dst0;
+};
+static thread_local SplitSeen g_seen[16];
+static thread_local int g_seen_next = 0;
+
+static unsigned long long split_hash() {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { h = (h ^ v) * 1099511628211ull; };
+    for (int i = 0; i < g_nsplit; ++i) {
+        const SplitJob &j = g_split.job[i];
+        mix((unsigned long long)(uintptr_t)j.src); mix((unsigned long long)(uintptr_t)j.dst);
+        mix(((unsigned long long)j.rows << 32) | (unsigned)j.cols); mix((unsigned long long)j.ld);
+    }
+    return h;
+}
+
 int split_run(cudaStream_t st) {
     if (g_nsplit == 0) return DPM_OK;
+    if (g_epoch != 0ull) {
+        const unsigned long long h = split_hash();
+        const float *dst0 = g_split.job[0].dst;
+        for (int i = 0; i < 16; ++i)
+            if (g_seen[i].dst0 == dst0) {
+                if (g_seen[i].epoch == g_epoch && g_seen[i].hash == h) return DPM_OK;  // still valid: no launch
+                g_seen[i].dst0 = nullptr;
+            }
+        g_seen[g_seen_next] = SplitSeen{g_epoch, h, dst0};
+        g_seen_next = (g_seen_next + 1) & 15;
+    }
     int maxn = 0;
     for (int i = 0; i < g_nsplit; ++i) maxn = g_split.job[i].rows * g_split.job[i].pad > maxn ? g_split.job[i].rows * g_split.job[i].pad : maxn;
     int gx = (maxn + 1023) / 1024;  // ~4 elements per thread for the largest matrix
@@ -632,3 +668,5 @@ extern "C" int dpm_debug_tc_profile(unsigned long long *out, int nctas) {
     return 0;
 }
 #endif
+
+extern "C" void dpm_set_weights_epoch(unsigned long long epoch) { dpm::g_epoch = epoch; }

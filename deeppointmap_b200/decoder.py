@@ -115,9 +115,13 @@ class Decoder(nn.Module):
                                        "(call .to(device) first)")
             dim_t = self._dim_t(device)
             arr = (ctypes.c_void_p * (len(ps) + 1))(*([p.data_ptr() for p in ps] + [dim_t.data_ptr()]))
-            c = (device, arr, len(ps) + 1, ps, dim_t)
+            c = (device, arr, len(ps) + 1, ps, dim_t, next(_C._epoch_ids))
             self._wcache = c
         return c[1], c[2]
+
+    def _fingerprint(self):
+        c = self._wcache
+        return (id(self), c[5], sum(p._version for p in c[3]))
 
     def _apply(self, fn, *a, **kw):
         self._wcache = None
@@ -187,10 +191,12 @@ class Decoder(nn.Module):
         if nb == 0:
             _C.check(-1, "registration workspace")
         ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr(dev)}")
+        lib.dpm_set_weights_epoch(_C.weights_epoch(self._fingerprint(), ws))
         with torch.cuda.device(dev):
             rc = lib.dpm_registration_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(),
                                               _C.ptr(sm), _C.ptr(dm), P, M, N, k, result.data_ptr(), conf.data_ptr(),
                                               ws.data_ptr(), ws.numel(), _C.stream_ptr())
+        lib.dpm_set_weights_epoch(0)
         _C.check(rc, "registration_forward")
         return result, conf
 
@@ -230,9 +236,11 @@ class Decoder(nn.Module):
         prob = torch.empty((P,), dtype=torch.float32, device=dev)
         nb = lib.dpm_loop_detection_workspace_bytes(ctypes.byref(self._desc), P, M, N)
         ws = _C.workspaces.get(dev, nb, f"dec{_C.stream_ptr(dev)}")
+        lib.dpm_set_weights_epoch(_C.weights_epoch(("loop",) + self._fingerprint(), ws))
         with torch.cuda.device(dev):
             rc = lib.dpm_loop_detection_forward(ctypes.byref(self._desc), warr, nw, src.data_ptr(), dst.data_ptr(),
                                                 _C.ptr(sm), _C.ptr(dm), P, M, N, prob.data_ptr(), ws.data_ptr(), ws.numel(),
                                                 _C.stream_ptr())
+        lib.dpm_set_weights_epoch(0)
         _C.check(rc, "loop_detection_forward")
         return prob

@@ -165,9 +165,15 @@ class Encoder(nn.Module):
                     raise RuntimeError("Encoder parameters must be contiguous fp32 tensors on the input's CUDA device "
                                        "(call .to(device) first)")
             arr = (ctypes.c_void_p * len(ps))(*[p.data_ptr() for p in ps])
-            c = (device, arr, len(ps), ps)
+            c = (device, arr, len(ps), ps, next(_C._epoch_ids))
             self._wcache = c
         return c[1], c[2]
+
+    def _fingerprint(self):
+        """identity of the current weight VALUES as far as torch can tell: this module, this pointer table, and the
+        parameters' in-place version counters (an optimiser step or `p.mul_()` bumps them)"""
+        c = self._wcache
+        return (id(self), c[4], sum(p._version for p in c[3]))
 
     def _apply(self, fn, *a, **kw):
         self._wcache = None
@@ -224,11 +230,13 @@ class Encoder(nn.Module):
         if nb == 0:
             _C.check(-1, "encoder workspace")
         ws = _C.workspaces.get(dev, nb, f"enc{_C.stream_ptr(dev)}")
+        lib.dpm_set_weights_epoch(_C.weights_epoch(self._fingerprint(), ws))  # unchanged weights + same scratch: no re-split
         with torch.cuda.device(dev):
             rc = lib.dpm_encoder_forward(ctypes.byref(self._desc), warr, nw, pts.data_ptr(), C, _C.ptr(pad), B, N,
                                          coor.data_ptr(), fea.data_ptr(), opad.data_ptr(), _C.ptr(desc),
                                          float(coor_scale), _C.ptr(tf), _C.ptr(tk), ws.data_ptr(), ws.numel(),
                                          _C.stream_ptr())
+        lib.dpm_set_weights_epoch(0)
         _C.check(rc, "encoder_forward")
         if self.trace:
             fps_idx, knn_idx, fo, ko = [], [], 0, 0

@@ -191,6 +191,12 @@ size_t dpm_encoder_workspace_bytes(const dpm_encoder_desc *desc, int B, int N);
 int dpm_encoder_num_weights(const dpm_encoder_desc *desc);
 int dpm_encoder_out_points(const dpm_encoder_desc *desc);
 
+/* Weight-copy reuse across calls (thread-local, default 0 = off): every encoder / decoder / linear_ws call writes
+ * hi / lo tf32 copies of its GEMM weights into the head of the caller's workspace.  With a NON-ZERO epoch the calling
+ * thread promises that neither the weight tensors nor that workspace changed since its previous call under the same
+ * epoch; the copy launch is then skipped.  Change the epoch (or set 0) whenever a weight or the workspace buffer does. */
+void dpm_set_weights_epoch(unsigned long long epoch);
+
 typedef struct dpm_decoder_desc {
     int in_channel, model_channel, attention_layers, heads; /* decoder.* ; heads = 8   */
     float tau, eps_offset;                                   /* loss.tau / eps_offset   */

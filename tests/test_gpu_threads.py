@@ -89,3 +89,40 @@ def test_step_is_cuda_graph_capturable(cfg, checkpoint):
             g.replay()
             torch.cuda.synchronize()
             assert torch.equal(out[0], want[0]) and torch.equal(out[1], want[1])
+
+
+def test_split_weight_reuse_follows_weight_updates(cfg):
+    """dpm_set_weights_epoch: a second call with unchanged weights into the same scratch skips the weight-split launch;
+    an in-place weight update (version counter) or a new scratch buffer brings it back, and the results follow."""
+    import copy
+    from oracle import model_ref as M
+    from deeppointmap_b200 import Encoder, _C, data
+    sd = M.random_weights(M.encoder_shapes(cfg), seed=21)
+    enc = Encoder(cfg).eval()
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV)
+    pts = data.kitti_shape_cloud(31, 8192)[None].to(DEV)
+
+    def run():
+        _C.launch_count_reset()
+        with torch.no_grad():
+            d = enc.descriptors(pts, None, 60.0)
+        torch.cuda.synchronize()
+        return d, _C.launch_count()
+
+    d1, n1 = run()
+    d2, n2 = run()
+    assert torch.equal(d1, d2)
+    if _C.REUSE_SPLIT:
+        assert n2 == n1 - 1                                   # the split launch is gone
+    with torch.no_grad():
+        enc.downsampler[1].sa.mlp[0].weight.mul_(1.5)         # in place: same pointer, new version
+    d3, n3 = run()
+    assert n3 == n1 and not torch.equal(d3, d1)
+    want = copy.deepcopy(sd)
+    want["downsampler.1.sa.mlp.0.weight"] = want["downsampler.1.sa.mlp.0.weight"] * 1.5
+    ref = M.descriptors(want, cfg, pts.cpu(), torch.zeros(1, 8192, dtype=torch.bool), "direct")
+    assert float((d3.cpu() - ref).abs().max() / ref.abs().max()) < 1e-4
+    _C.workspaces.release()                                   # new scratch buffer: split again
+    d4, n4 = run()
+    assert n4 == n1 and torch.equal(d4, d3)
