@@ -106,7 +106,8 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // ---- per-cloud uniform cell grid (grid.cu) ------------------------------------------------
 constexpr int GRID_MAXCELL = 32768;   // cells per cloud (the cell size grows until the grid fits)
-constexpr int GRID_MAX_N = 262144;    // 1024 buckets x 32 lanes x 8 points per lane
+constexpr int GRID_MAX_N = 1048576;          // 1024 buckets x 32 lanes x 32 points per lane
+constexpr int GRID_CLUSTER_MAX_N = 262144;   // the cluster / tuned one-SM FPS kernels: <= 8 points per lane
 constexpr int GRID_MIN_N = 2048;      // below this the brute-force / register kernels win
 struct GridDesc {
     float ox, oy, oz, inv_h;  // cell of p = floor((p - o) * inv_h), x fastest
@@ -125,7 +126,7 @@ struct GridWs {
     int npad;
 };
 inline int grid_npad(int N) { return (N + 255) & ~255; }
-inline int grid_ppl(int N) { return N <= 32768 ? 1 : (N <= 65536 ? 2 : (N <= 131072 ? 4 : 8)); }
+inline int grid_ppl(int N) { return N <= 32768 ? 1 : (N <= 65536 ? 2 : (N <= 131072 ? 4 : (N <= 262144 ? 8 : (N <= 524288 ? 16 : 32)))); }
 size_t grid_ws_bytes(int B, int N);
 bool grid_ws_carve(Arena &a, int B, int N, GridWs *g);
 // hmin: lower bound of the cell size (1.001 x the largest query radius served by this grid; 0 = FPS only)

@@ -672,7 +672,7 @@ static int fps_grid_cluster_t(const GridWs &g, const float4 *xyz4, int B, int N,
 
 int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                             float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
-    if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
+    if (N > GRID_CLUSTER_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_CLUSTER_MAX_N);
     prof_note(N, K);
     switch (grid_ppl(N)) {
         case 1: return fps_grid_cluster_t<1, true, GeoCluster>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
@@ -686,7 +686,7 @@ int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, i
 // the same algorithm with one CTA (one SM) per cloud, tiles in L2: the throughput mapping
 int fps_grid_onesm_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                           float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
-    if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
+    if (N > GRID_CLUSTER_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_CLUSTER_MAX_N);
     prof_note(N, K);
     switch (grid_ppl(N)) {
         case 1: return fps_grid_cluster_t<1, false, GeoOneSm>(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);

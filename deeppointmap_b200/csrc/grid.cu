@@ -235,7 +235,7 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 // Letting untouched warps republish their previous record instead of recomputing it: 4.89 -> 5.36 ms.
 // ---------------------------------------------------------------------------------------
 template <int PPL, int T, int BPT, int D>
-__global__ void __launch_bounds__(T, 1)
+__global__ void __launch_bounds__(T, (T >= 1024 || PPL >= 16) ? 1 : 2)  // narrower teams keep <= 64 registers (the rest of the SM stays free), huge clouds get 128
 fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
                 const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
                 int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
@@ -430,7 +430,7 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
                     float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
     if (B <= 0 || N <= 0 || K <= 0) return fail(DPM_ERR_SHAPE, "fps: bad shape B=%d N=%d K=%d", B, N, K);
     if (N > GRID_MAX_N) return fail(DPM_ERR_UNSUPPORTED, "fps: N=%d exceeds the limit %d", N, GRID_MAX_N);
-    if (fps_cluster_mode(B))  // few clouds: 8 SMs per cloud instead of one (fps_cluster.cu)
+    if (fps_cluster_mode(B) && N <= GRID_CLUSTER_MAX_N)  // few clouds: 8 SMs per cloud instead of one (fps_cluster.cu)
         return fps_grid_cluster_launch(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
     // Measured and rejected (round 2): the cluster kernel's algorithm (broadcast arg-max, two picks per round, mbarrier
     // record exchange) in a ONE-CTA geometry of 32 warps, fps_grid_onesm_launch: bit-exact, but 6.4 ms against this
@@ -438,16 +438,25 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
     // costs more than one __syncthreads, and the bucket maxima sit on the critical path when the tiles are not in
     // shared memory.  DPM_FPS_ONESM=1 selects it for A/B runs.
     static const bool onesm_new = getenv("DPM_FPS_ONESM") && atoi(getenv("DPM_FPS_ONESM")) == 1;
-    if (onesm_new) return fps_grid_onesm_launch(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
+    if (onesm_new && N <= GRID_CLUSTER_MAX_N) return fps_grid_onesm_launch(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
     const int ppl = grid_ppl(N);
     prof_note(N, K);
 #define DPM_FG_ARGS g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, new_pad, new_len32
+    // team width: 1024 threads own one bucket each; 512 / 256 threads own two / four and leave the rest of the SM's
+    // threads and registers to the other streams' kernels (DPM_FPS_T, A/B switch)
+    static const int team = getenv("DPM_FPS_T") ? atoi(getenv("DPM_FPS_T")) : 1024;
 #define DPM_FG_CASE(p)                                                \
     case p:                                                           \
-        fps_grid_kernel<p, 1024, 1, (p <= 2 ? 2 : 1)><<<B, 1024, 0, st>>>(DPM_FG_ARGS); \
+        if (team == 512) fps_grid_kernel<p, 512, 2, 1><<<B, 512, 0, st>>>(DPM_FG_ARGS); \
+        else if (team == 256) fps_grid_kernel<p, 256, 4, 1><<<B, 256, 0, st>>>(DPM_FG_ARGS); \
+        else fps_grid_kernel<p, 1024, 1, (p <= 2 ? 2 : 1)><<<B, 1024, 0, st>>>(DPM_FG_ARGS); \
         break;
     switch (ppl) {
         DPM_FG_CASE(1) DPM_FG_CASE(2) DPM_FG_CASE(4) DPM_FG_CASE(8)
+        // clouds of 262 145 .. 1 048 576 points (beyond any LiDAR frame; pytorch3d has no limit): the same kernel with
+        // 16 / 32 points per lane, two buckets per thread so that a thread may hold 128 registers
+        case 16: fps_grid_kernel<16, 512, 2, 1><<<B, 512, 0, st>>>(DPM_FG_ARGS); break;
+        case 32: fps_grid_kernel<32, 512, 2, 1><<<B, 512, 0, st>>>(DPM_FG_ARGS); break;
         default:
             return fail(DPM_ERR_UNSUPPORTED, "fps: no kernel for %d points per lane", ppl);
     }

@@ -196,6 +196,83 @@ knn_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ p4, int S, 
     }
 }
 
+// K > 32 (pytorch3d knn_points has no limit on K; nothing in the reference asks for more than 32): warp per query,
+// ceil(K / 32) passes over the cloud.  Pass p keeps the 32 smallest keys (d2, index) that come AFTER the last key of
+// pass p - 1 in the same total order, in the same lane-distributed list as knn_kernel, so the concatenation of the
+// passes is the ascending top K.  Points are read straight from L2; O(N K / 32) per query -- a completeness path.
+__global__ void __launch_bounds__(KNN_T)
+knn_big_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ p4, int S, int N,
+               const int *__restrict__ qlen32, const int *__restrict__ plen32, int K, float cap, int mode,
+               int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ d2out) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * KNN_WARPS + (threadIdx.x >> 5);
+    if (s >= S) return;  // warp-uniform
+    const int len = plen32 ? min(plen32[b], N) : N;
+    const int qlen = qlen32 ? min(qlen32[b], S) : S;
+    const size_t o = ((size_t)b * S + s) * K;
+    const float INF = __int_as_float(0x7f800000);
+    const float4 *pts = p4 + (size_t)b * N;
+    int done = 0;  // slots written so far
+    int first = 0;
+    if (s < qlen) {
+        const float4 c = q4[(size_t)b * S + s];
+        float pd = -1.f;  // last key of the previous pass: every d2 is >= 0, so the first pass takes everything
+        int pi = -1;
+        while (done < K) {
+            const int kk = min(32, K - done);
+            const unsigned kmask = kk >= 32 ? 0xffffffffu : ((1u << kk) - 1u);
+            float ld = INF, thr = cap;
+            int li = 0;
+            for (int off = 0; off < len; off += 32) {
+                const int i = off + lane;
+                float d = INF;
+                if (i < len) {
+                    const float4 p = pts[i];
+                    d = d2_exact(c.x, c.y, c.z, p.x, p.y, p.z);
+                }
+                const bool after = d > pd || (d == pd && i > pi);
+                const unsigned cm = __ballot_sync(0xffffffffu, after && d < thr);
+                if (cm) knn_insert(cm, d, i, ld, li, thr, kk, kmask, lane);
+            }
+            const int count = __popc(__ballot_sync(0xffffffffu, ld < INF) & kmask);
+            if (done == 0) first = __shfl_sync(0xffffffffu, li, 0);
+            if (lane < count) {
+                if (idx64) idx64[o + done + lane] = (int64_t)li;
+                if (idx32) idx32[o + done + lane] = li;
+                if (d2out) d2out[o + done + lane] = ld;
+            }
+            done += count;
+            if (count < kk) break;  // the cloud (or the radius) is exhausted
+            pd = __shfl_sync(0xffffffffu, ld, kk - 1);
+            pi = __shfl_sync(0xffffffffu, li, kk - 1);
+        }
+        if (mode == KNN_MODE_HYBRID && done == 0 && len > 0) {
+            // nothing inside the radius: slot 0 of the uncapped kNN is the nearest point
+            unsigned long long best = ~0ull;
+            for (int i = lane; i < len; i += 32) {
+                const float4 p = pts[i];
+                const float dd = d2_exact(c.x, c.y, c.z, p.x, p.y, p.z);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(dd) << 32) | (unsigned)i;
+                best = key < best ? key : best;
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, best, sft);
+                best = o2 < best ? o2 : best;
+            }
+            first = (int)(unsigned)best;
+        }
+    }
+    // padding: hybrid repeats slot 0 over the slots a cloud of `len` points could fill, everything else is 0
+    const int kvalid = (mode == KNN_MODE_HYBRID && s < qlen) ? min(len, K) : 0;
+    for (int k = done + lane; k < K; k += 32) {
+        const int oi = k < kvalid ? first : 0;
+        if (idx64) idx64[o + k] = (int64_t)oi;
+        if (idx32) idx32[o + k] = oi;
+        if (d2out) d2out[o + k] = 0.f;
+    }
+}
+
 template <int QW>
 static int knn_launch_t(const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32,
                         const int *plen32, int K, float cap, int mode, int64_t *idx64, int32_t *idx32,
@@ -217,11 +294,18 @@ static int knn_launch_t(const float4 *q4, const float4 *p4, int B, int S, int N,
 int knn_launch(const float4 *q4, const float4 *p4, int B, int S, int N, const int *qlen32, const int *plen32,
                int K, float r2, int mode, int64_t *idx64, int32_t *idx32, float *d2out, cudaStream_t st) {
     if (B <= 0 || S <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "knn: bad shape B=%d S=%d N=%d", B, S, N);
-    if (K <= 0 || K > 32) return fail(DPM_ERR_UNSUPPORTED, "knn: K=%d not in 1..32", K);
+    if (K <= 0) return fail(DPM_ERR_SHAPE, "knn: K=%d", K);
     float cap = __builtin_inff();
     if (mode == KNN_MODE_HYBRID) {
         // keep d2 <= r2  <=>  d2 < nextafter(r2, +inf)
         cap = r2 >= 0.f ? __builtin_nextafterf(r2, __builtin_inff()) : 0.f;
+    }
+    if (K > 32) {
+        prof_note(S, N);
+        dim3 grid((S + KNN_WARPS - 1) / KNN_WARPS, B, 1);
+        knn_big_kernel<<<grid, KNN_T, 0, st>>>(q4, p4, S, N, qlen32, plen32, K, cap, mode, idx64, idx32, d2out);
+        DPM_CHECK_LAUNCH("knn", st);
+        return DPM_OK;
     }
     const long long sms = device_sm_count();
     const long long warps = (long long)B * ((S + KNN_WARPS - 1) / KNN_WARPS);  // CTAs at QW=1

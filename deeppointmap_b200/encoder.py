@@ -31,12 +31,12 @@ class _LNHolder(nn.Module):
         self.ln = nn.LayerNorm(channels)
 
 
-def _mlp_holder(cin: int, channels: List[int], dim: int, drop_last_act: bool = False) -> nn.Sequential:
+def _mlp_holder(cin: int, channels: List[int], dim: int, drop_last_act: bool = False, bias: bool = True) -> nn.Sequential:
     """Parameter layout of build_mlp (utils.py:358-389): conv, norm, act triplets (acts hold nothing)."""
     conv = nn.Conv1d if dim == 1 else nn.Conv2d
     mods = []
     for c in channels:
-        mods += [conv(cin, c, kernel_size=1, bias=True), _LNHolder(c), nn.Identity()]
+        mods += [conv(cin, c, kernel_size=1, bias=bias), _LNHolder(c), nn.Identity()]
         cin = c
     if drop_last_act:
         mods = mods[:-1]
@@ -44,36 +44,36 @@ def _mlp_holder(cin: int, channels: List[int], dim: int, drop_last_act: bool = F
 
 
 class _SA(nn.Module):
-    def __init__(self, cin):
+    def __init__(self, cin, bias=True):
         super().__init__()
-        self.mlp = _mlp_holder(cin + 3, [2 * cin], 2)
+        self.mlp = _mlp_holder(cin + 3, [2 * cin], 2, bias=bias)
 
 
 class _LA(nn.Module):
-    def __init__(self, c):
+    def __init__(self, c, bias=True):
         super().__init__()
-        self.mlp = _mlp_holder(c + 3, [c], 2)
+        self.mlp = _mlp_holder(c + 3, [c], 2, bias=bias)
 
 
 class _IRM(nn.Module):
-    def __init__(self, c, expansion):
+    def __init__(self, c, expansion, bias=True):
         super().__init__()
-        self.la = _LA(c)
-        self.pw_conv = _mlp_holder(c, [c * expansion, c], 1, drop_last_act=True)
+        self.la = _LA(c, bias)
+        self.pw_conv = _mlp_holder(c, [c * expansion, c], 1, drop_last_act=True, bias=bias)
 
 
 class _Stage(nn.Module):
-    def __init__(self, cin, n_blocks, expansion):
+    def __init__(self, cin, n_blocks, expansion, bias=True):
         super().__init__()
-        self.sa = _SA(cin)
-        irm = [_IRM(2 * cin, expansion) for _ in range(n_blocks - 1)]
+        self.sa = _SA(cin, bias)
+        irm = [_IRM(2 * cin, expansion, bias) for _ in range(n_blocks - 1)]
         self.irm = nn.Sequential(*irm) if irm else nn.Identity()
 
 
 class _FP(nn.Module):
-    def __init__(self, cin, cout):
+    def __init__(self, cin, cout, bias=True):
         super().__init__()
-        self.mlp = _mlp_holder(cin, [cout, cout], 1)
+        self.mlp = _mlp_holder(cin, [cout, cout], 1, bias=bias)
 
 
 class Encoder(nn.Module):
@@ -93,8 +93,10 @@ class Encoder(nn.Module):
         expansion = int(_cfg_get(cfg, "expansion"))
         norm = str(_cfg_get(cfg, "norm", "LN")).lower()
         bias = bool(_cfg_get(cfg, "bias", True))
-        if norm != "ln" or not bias:
-            raise NotImplementedError("libdpm_b200 implements the shipped configuration (norm: LN, bias: True)")
+        if norm != "ln":
+            raise NotImplementedError("libdpm_b200 implements LayerNorm blocks (norm: LN, the shipped configuration); "
+                                      "the BatchNorm / InstanceNorm variants of build_mlp are not on the CUDA path")
+        self._bias = bias
         for s in (_cfg_get(cfg, "sample", None) or []):
             t = _cfg_get(s, "type", "fps-t3d")
             if t not in ("fps", "fps-t3d"):
@@ -119,12 +121,12 @@ class Encoder(nn.Module):
         self.upsampler = nn.ModuleList()
         w = width
         for i in range(self.downsample_layers):
-            self.downsampler.append(_Stage(w, len(radius_list[i]), expansion))
+            self.downsampler.append(_Stage(w, len(radius_list[i]), expansion, bias))
             w *= 2
         up_in = w
         for _ in range(self.upsample_layers):
             up_out = max(self.out_channel, w // 2)
-            self.upsampler.append(_FP(up_in + w // 2, up_out))
+            self.upsampler.append(_FP(up_in + w // 2, up_out, bias))
             w //= 2
             up_in = up_out
         self.final_channel = up_in if self.upsample_layers > 0 else w
@@ -154,7 +156,22 @@ class Encoder(nn.Module):
             p = f"upsampler.{i}"
             names += [p + ".mlp.0.weight", p + ".mlp.0.bias"] + ln(p + ".mlp.1")
             names += [p + ".mlp.3.weight", p + ".mlp.3.bias"] + ln(p + ".mlp.4")
-        return [sd[n] for n in names]
+        if self._bias:
+            return [sd[n] for n in names]
+        # bias: False (utils.py:358-389 builds the convolutions without one): the kernels take a pointer per slot of
+        # the canonical table, so the missing conv biases are zero vectors (x + 0 is exact) kept as non-persistent
+        # buffers -- they follow .to(device) and stay out of the state_dict
+        out = []
+        for i, n in enumerate(names):
+            if n in sd:
+                out.append(sd[n])
+                continue
+            c = sd[names[i - 1]].shape[0]  # the conv weight right before it
+            key = f"_zero_bias_{c}"
+            if not hasattr(self, key):
+                self.register_buffer(key, torch.zeros(c, dtype=torch.float32, device=sd[names[i - 1]].device), persistent=False)
+            out.append(getattr(self, key))
+        return out
 
     def _weights(self, device):
         c = self._wcache

@@ -105,6 +105,7 @@ int oracle_fps(const float *points, int B, int N, int D, const int64_t *lengths,
 int oracle_knn(const float *p1, int D1, const float *p2, int D2, int B, int S, int N,
                const int64_t *lengths2, int K, int64_t *idx_out, float *d2_out) {
     if (B < 0 || S < 0 || N <= 0 || K <= 0 || D1 < 3 || D2 < 3) return -1;
+    if (K > 4096) return -3;
 #pragma omp parallel for collapse(2) schedule(dynamic, 16)
     for (int b = 0; b < B; ++b) {
         for (int s = 0; s < S; ++s) {
@@ -112,10 +113,10 @@ int oracle_knn(const float *p1, int D1, const float *p2, int D2, int B, int S, i
             const float *P = p2 + (size_t)b * N * D2;
             int64_t len = lengths2 ? lengths2[b] : N;
             if (len > N) len = N;
-            float bd[64];
-            int64_t bi[64];
+            const int KK = K;
+            float bd[KK]; /* K is bounded by the caller (index_ops.py: K <= 4096) */
+            int64_t bi[KK];
             int cnt = 0;
-            const int KK = K > 64 ? 64 : K;
             for (int64_t i = 0; i < len; ++i) {
                 float d = d2_fast(Q[0], Q[1], Q[2], P[i * D2], P[i * D2 + 1], P[i * D2 + 2]);
                 if (cnt == KK && !(d < bd[KK - 1])) continue; /* ties keep the lower index */
@@ -137,7 +138,7 @@ int oracle_knn(const float *p1, int D1, const float *p2, int D2, int B, int S, i
             }
         }
     }
-    return K > 64 ? -3 : 0;
+    return 0;
 }
 
 /* Querier.hybrid_query_t3d: kNN, then every slot with d2 > r2 takes slot 0's index.

@@ -162,3 +162,34 @@ def test_per_stage_features_elementwise(cfg, checkpoint, golden_sample, n_stages
     bound = 1e-4 * torch.maximum(torch.maximum(want.abs(), rms_c.expand_as(want)), floor.expand_as(want))
     bad = (got - want).abs() > bound
     assert not bool(bad.any()), (int(bad.sum()), float(((got - want).abs() / bound).max()))
+
+
+def test_bias_false_equals_zero_biases():
+    """`encoder.bias: False` (network/encoder/utils.py:358-389: convolutions without a bias): the same kernels with
+    zero vectors in the bias slots -- bit-identical to a bias: True model whose conv biases are zero, and within the
+    parity bar of the oracle evaluated on that state dict."""
+    import copy
+    cfg = _small_cfg()
+    full = Encoder(cfg).eval()
+    full.load_state_dict(M.random_weights(M.encoder_shapes(cfg), seed=5), strict=True)
+    with torch.no_grad():
+        for n, p in full.named_parameters():
+            if n.endswith(".bias") and ".ln." not in n and n != "point_mlp0.bias":
+                p.zero_()
+    cfg2 = copy.deepcopy(cfg)
+    cfg2.encoder.bias = False
+    free = Encoder(cfg2).eval()
+    sd_free = {k: v for k, v in full.state_dict().items() if k in free.state_dict()}
+    assert len(sd_free) < len(full.state_dict())
+    free.load_state_dict(sd_free, strict=True)
+    full, free = full.to(DEV), free.to(DEV)
+    pts = torch.stack([data.kitti_shape_cloud(3, 2048), data.uniform_cube_cloud(4, 2048)])
+    pad = torch.zeros(2, 2048, dtype=torch.bool)
+    pad[1, 1500:] = True
+    with torch.no_grad():
+        a = full(pts.to(DEV), pad.to(DEV))
+        b = free(pts.to(DEV), pad.to(DEV))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    want = M.encoder_forward({k: v.cpu() for k, v in full.state_dict().items()}, cfg, pts, pad, "direct")
+    assert rel_err(b[1].cpu(), want[1]) < TOL

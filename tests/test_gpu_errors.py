@@ -49,8 +49,8 @@ def test_python_layer_exception_types(cfg):
         ops.sample_farthest_points(torch.zeros(1, 8, 2, device=DEV), K=2)
     with pytest.raises(NotImplementedError):
         ops.sample_farthest_points(torch.zeros(1, 8, 3, device=DEV), K=2, random_start_point=True)
-    with pytest.raises(NotImplementedError):
-        ops.knn_points(torch.zeros(1, 8, 3, device=DEV), torch.zeros(1, 8, 3, device=DEV), K=33)
+    with pytest.raises(ValueError):
+        ops.knn_points(torch.zeros(1, 8, 3, device=DEV), torch.zeros(1, 8, 3, device=DEV), K=0)
     with pytest.raises(ValueError):
         ops.information_matrix(torch.zeros(2, 8, device=DEV), torch.zeros(3, 8, device=DEV), torch.eye(4))
     enc, dec = Encoder(cfg).eval().to(DEV), Decoder(cfg).eval().to(DEV)

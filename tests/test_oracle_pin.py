@@ -418,3 +418,28 @@ def test_low_pass_filter_matches_reference():
     kept, mask, sim, thr = lowpass_ref.low_pass_filter(xyz, 0.5, 16, 2.0, 4)
     assert 0 < int((~mask).sum()) < 1500
     assert torch.equal(out.xyz, kept)
+
+
+@needs_ref
+def test_bias_false_state_dict_matches_the_reference(reference):
+    """`encoder.bias: False` (network/encoder/encoder.py:22, utils.py:358-389): the drop-in holds the same parameters
+    as the reference built with that flag -- no conv biases except the stem's -- and still fills a full pointer table."""
+    import copy
+    import yaml
+    from easydict import EasyDict
+    from network.encoder.encoder import Encoder as RefEncoder
+    from deeppointmap_b200 import Encoder
+    cfg = EasyDict(yaml.safe_load(open(f"{REF}/configs/infer/DeepPointMap_B_Main_SemanticKITTI.yaml")))
+    cfg.encoder.bias = False
+    ref = RefEncoder(copy.deepcopy(cfg))
+    ours = Encoder(copy.deepcopy(cfg))
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert list(rs.keys()) == list(os_.keys())
+    assert all(rs[k].shape == os_[k].shape for k in rs)
+    assert "point_mlp0.bias" in os_ and "downsampler.0.sa.mlp.0.bias" not in os_
+    ours.load_state_dict(rs, strict=True)
+    table = ours._ordered_params()
+    full = Encoder(EasyDict(yaml.safe_load(open(f"{REF}/configs/infer/DeepPointMap_B_Main_SemanticKITTI.yaml"))))
+    assert len(table) == len(full._ordered_params())
+    assert [tuple(t.shape) for t in table] == [tuple(t.shape) for t in full._ordered_params()]
+    assert list(ours.state_dict().keys()) == list(rs.keys())  # the zero vectors stay out of the state_dict
