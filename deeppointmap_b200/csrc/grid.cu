@@ -36,7 +36,8 @@ __device__ __forceinline__ int cell_coord_free(float p, float o, float inv_h, in
     return (int)fminf(fmaxf(t, -2.f), (float)(g + 1));
 }
 
-__global__ void __launch_bounds__(1024)
+template <int T>
+__global__ void __launch_bounds__(T)
 grid_bbox_kernel(const float4 *__restrict__ xyz4, int N, const int *__restrict__ len32, float hmin,
                  GridDesc *__restrict__ desc) {
     __shared__ float red[6][32];
@@ -45,7 +46,7 @@ grid_bbox_kernel(const float4 *__restrict__ xyz4, int N, const int *__restrict__
     const float4 *pts = xyz4 + (size_t)b * N;
     const float INF = __int_as_float(0x7f800000);
     float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
-    for (int i = tid; i < len; i += 1024) {
+    for (int i = tid; i < len; i += T) {
         const float4 p = pts[i];
         lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
         lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
@@ -63,7 +64,7 @@ grid_bbox_kernel(const float4 *__restrict__ xyz4, int N, const int *__restrict__
     __syncthreads();
     if (tid == 0) {
         for (int a = 0; a < 3; ++a)
-            for (int w = 1; w < 32; ++w) {
+            for (int w = 1; w < T / 32; ++w) {
                 red[a][0] = fminf(red[a][0], red[a][w]);
                 red[3 + a][0] = fmaxf(red[3 + a][0], red[3 + a][w]);
             }
@@ -114,14 +115,15 @@ grid_count_kernel(const float4 *__restrict__ xyz4, int N, const GridDesc *__rest
 }
 
 // exclusive scan of the per-cell counts (in place) + a copy as the scatter cursor
-__global__ void __launch_bounds__(1024)
+template <int T>
+__global__ void __launch_bounds__(T)
 grid_scan_kernel(const GridDesc *__restrict__ desc, int *__restrict__ cell_start, int *__restrict__ cursor) {
     __shared__ int wsum[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncell = desc[b].ncell;
     int *cs = cell_start + (size_t)b * (GRID_MAXCELL + 1);
     int *cu = cursor + (size_t)b * (GRID_MAXCELL + 1);
-    const int per = (ncell + 1023) / 1024;
+    const int per = (ncell + T - 1) / T;
     const int c0 = tid * per, c1 = min(ncell, c0 + per);
     int s = 0;
     for (int c = c0; c < c1; ++c) s += cs[c];
@@ -134,7 +136,7 @@ grid_scan_kernel(const GridDesc *__restrict__ desc, int *__restrict__ cell_start
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        int v = wsum[lane], iv = v;
+        int v = lane < T / 32 ? wsum[lane] : 0, iv = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, iv, o);
@@ -150,7 +152,7 @@ grid_scan_kernel(const GridDesc *__restrict__ desc, int *__restrict__ cell_start
         cu[c] = run;
         run += n;
     }
-    if (tid == 1023) cs[ncell] = run;  // the last thread's running sum is the total (its range may be empty)
+    if (tid == T - 1) cs[ncell] = run;  // the last thread's running sum is the total (its range may be empty)
 }
 
 __global__ void __launch_bounds__(256)
@@ -198,13 +200,18 @@ bool grid_ws_carve(Arena &a, int B, int N, GridWs *g) {
 int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float hmin, const GridWs &g, cudaStream_t st) {
     if (B <= 0 || N <= 0) return fail(DPM_ERR_SHAPE, "grid: bad shape B=%d N=%d", B, N);
     prof_note(N, 0);
-    grid_bbox_kernel<<<B, 1024, 0, st>>>(xyz4, N, len32, hmin, g.desc);
+    // team width of the two one-CTA-per-cloud kernels (DPM_GRID_T, A/B switch): a 1024-thread CTA needs half an SM's
+    // thread slots at once, which it rarely finds while other streams' kernels are resident
+    static const int team = getenv("DPM_GRID_T") ? atoi(getenv("DPM_GRID_T")) : 1024;
+    if (team == 256) grid_bbox_kernel<256><<<B, 256, 0, st>>>(xyz4, N, len32, hmin, g.desc);
+    else grid_bbox_kernel<1024><<<B, 1024, 0, st>>>(xyz4, N, len32, hmin, g.desc);
     DPM_CHECK_LAUNCH("grid_bbox", st);
     DPM_CHECK_CUDA(cudaMemsetAsync(g.cell_start, 0, sizeof(int) * (size_t)B * (GRID_MAXCELL + 1), st));
     dim3 grid((N + 255) / 256, B, 1);
     grid_count_kernel<<<grid, 256, 0, st>>>(xyz4, N, g.desc, g.cell_start, g.cellid);
     DPM_CHECK_LAUNCH("grid_count", st);
-    grid_scan_kernel<<<B, 1024, 0, st>>>(g.desc, g.cell_start, g.cursor);
+    if (team == 256) grid_scan_kernel<256><<<B, 256, 0, st>>>(g.desc, g.cell_start, g.cursor);
+    else grid_scan_kernel<1024><<<B, 1024, 0, st>>>(g.desc, g.cell_start, g.cursor);
     DPM_CHECK_LAUNCH("grid_scan", st);
     dim3 grid2((g.npad + 255) / 256, B, 1);
     grid_scatter_kernel<<<grid2, 256, 0, st>>>(xyz4, N, g.npad, g.desc, g.cellid, g.cursor, g.sorted);
@@ -556,6 +563,8 @@ knn_grid_kernel(const float4 *__restrict__ q4, const float4 *__restrict__ sorted
         const int ki = __shfl_sync(0xffffffffu, li, K - 1);
         if (kd < INF) { thrd = kd; thri = ki; }
     };
+    // (visiting the query's own x-row first so that the bound tightens sooner was measured: no change -- at the encoder's
+    // radii most queries see fewer than K points inside the radius, so every in-radius candidate passes in any order)
     for (int r = 0; r < 9; ++r) {
         const int st = __shfl_sync(0xffffffffu, rs, r), en = __shfl_sync(0xffffffffu, re, r);
         for (int i0 = st; i0 < en; i0 += 32) {
