@@ -41,8 +41,13 @@ def parse():
     ap.add_argument("--streams", type=int, default=0,
                     help="CUDA streams the steps are issued on round-robin (independent frame sequences, like the "
                          "reference's multi-agent mode): the latency-bound FPS chain of one step overlaps the "
-                         "throughput-bound kernels of another.  0 = auto: 6, 5 or 4, whichever divides --steps (no "
-                         "partially filled last round inside the timed region), else 4")
+                         "throughput-bound kernels of another.  0 = auto: with the packed FPS mapping 8 (10 when only 10 "
+                         "divides --steps), else 6, 5 or 4, whichever divides --steps (no partially filled last round "
+                         "inside the timed region)")
+    ap.add_argument("--fps-mode", type=int, default=3, choices=[0, 1, 2, 3],
+                    help="dpm_set_fps_mode for the multi-stream legs (headline, sustained, e2e, kernel profile): 3 = packed, two "
+                         "clouds per SM (less SM time per batch, longer FPS latency: pays with >= 8 streams in flight); 0 = the "
+                         "library's automatic choice.  The one-stream legs (batch1, strong, caller sizes) always run on 0")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -510,12 +515,35 @@ def main():
     dev_pool = [h.to(dev) for h in host_pool]
     pool_mb = nslots * bytes_per_batch / 2 ** 20
 
-    NS = args.streams if args.streams > 0 else next((c for c in (6, 5, 4) if K % c == 0), 4)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
-    descbufs = [torch.zeros((F + 1, Cd, S), dtype=torch.float32, device=dev) for _ in range(NS)]
+    # The packed FPS mapping (two clouds per SM) trades FPS latency for SM time: it needs >= 8 streams in flight AND a
+    # pipeline long enough to leave the lock-step start behind (measured: 7480 against 7240 frames/s at 200 steps, but
+    # 6910 against 7160 at 20 steps).  So a leg of >= 64 steps runs packed on 8 streams, a shorter one on the library's
+    # automatic mapping with 6 / 5 / 4 streams.
+    PACK_MIN_STEPS = 64
+    can_pack = args.fps_mode == 3 and F > int(_C.lib().dpm_fps_cluster_capacity())
+
+    def leg_config(nsteps, flexible=False):
+        """-> (packed?, streams) of a multi-stream leg of `nsteps` steps (flexible: the caller rounds the steps up to
+        whole rounds, so the stream count need not divide them)"""
+        if can_pack and nsteps >= PACK_MIN_STEPS:
+            return True, (args.streams if args.streams > 0 else (8 if flexible or nsteps % 8 == 0 or nsteps % 10 else 10))
+        return False, (args.streams if args.streams > 0 else next((c for c in (6, 5, 4) if nsteps % c == 0), 4))
+
+    packed, NS = leg_config(K)
+    NSMAX = max(NS, 10 if can_pack else NS)
+    from deeppointmap_b200 import ops as _ops
+
+    def fps_mode_multi(pk=None):   # the legs that keep several streams of batches in flight
+        pk = packed if pk is None else pk
+        _ops.set_fps_mode(3 if pk else (0 if args.fps_mode == 3 else args.fps_mode))
+
+    def fps_mode_auto():    # one-stream legs: the library's own choice (cluster per cloud for small batches)
+        _ops.set_fps_mode(0)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NSMAX)]
+    descbufs = [torch.zeros((F + 1, Cd, S), dtype=torch.float32, device=dev) for _ in range(NSMAX)]
     descbuf = descbufs[0]
     gathered = [torch.empty((world * F, _C.REG_STRIDE), dtype=torch.float32, device=dev) if world > 1 else None
-                for _ in range(NS)]
+                for _ in range(NSMAX)]
     k_pairs = dec.num_pairs(0.5, S, S)
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
@@ -541,20 +569,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(n, first, fn):
-        """n steps round-robin over the streams; returns device ms from a common start event to the
+    def run_steps(n, first, fn, ns=None):
+        """n steps round-robin over the first `ns` streams; returns device ms from a common start event to the
         last stream's end (events on the launching streams)"""
+        ns = NS if ns is None else ns
         cur = torch.cuda.current_stream()
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record(cur)
-        for st in streams:
+        for st in streams[:ns]:
             st.wait_event(ev0)
         for i in range(n):
-            q = i % NS
+            q = i % ns
             with torch.cuda.stream(streams[q]):
                 fn(first + i, q)
-        for st in streams + ([comm] if comm is not None else []):  # the gathered poses are part of the job
+        for st in streams[:ns] + ([comm] if comm is not None else []):  # the gathered poses are part of the job
             e = torch.cuda.Event()
             e.record(st)
             cur.wait_event(e)
@@ -562,6 +591,7 @@ def main():
         return ev0, ev1
 
     with torch.no_grad():
+        fps_mode_multi()
         # every stream is warmed (its workspace allocated) before the timed region; one extra step staggers them
         run_steps(max(W, NS) + (1 if NS > 1 else 0), 0, lambda i, q: step(dev_pool[i % nslots], q))
         # rank 0 reports the clocks (NVML polling stays off the other ranks); nvmlInit happens BEFORE the barrier so that
@@ -589,10 +619,15 @@ def main():
         if not args.no_extra:
             reps = max(1, int(-(-args.sustain_s * 1e3 // max(total_ms, 1e-3))))
             ks = reps * K
+            spk, sns = leg_config(ks, flexible=True)
+            ks = -(-ks // sns) * sns  # whole rounds
+            fps_mode_multi(spk)
+            if sns > NS or spk != packed:  # streams / kernels the headline did not warm
+                run_steps(sns + 1, 0, lambda i, q: step(dev_pool[i % nslots], q), sns)
             clk2 = ClockSampler(local if rank == 0 else -1)
             barrier()
             with clk2 as c2:
-                s0, s1 = run_steps(ks, W + K, lambda i, q: step(dev_pool[i % nslots], q))
+                s0, s1 = run_steps(ks, W + K, lambda i, q: step(dev_pool[i % nslots], q), sns)
                 barrier()
             sms = s0.elapsed_time(s1)
             ts = torch.tensor([sms], dtype=torch.float64, device=dev)
@@ -600,12 +635,15 @@ def main():
                 dist.all_reduce(ts, op=dist.ReduceOp.MAX)
             sms = float(ts.item())
             sustained = {"steps": ks, "seconds": sms * 1e-3, "value": world * F * ks / (sms * 1e-3), "unit": UNIT,
-                         "ms_per_step": sms / ks, "clocks": c2.summary(),
-                         "note": "same loop as the headline, run long enough for clocks / power to settle"}
+                         "ms_per_step": sms / ks, "clocks": c2.summary(), "streams_per_gpu": sns,
+                         "fps_mode": "packed: two clouds per SM (dpm_set_fps_mode(3))" if spk else "automatic",
+                         "note": "same loop as the headline, run long enough for clocks / power to settle; from 64 steps "
+                                 "on a leg runs the packed FPS mapping on 8 streams (see config.fps_mode)"}
 
         # ---- strong scaling (BASELINE configs[3] as written): --strong-frames GLOBAL frames sharded over the ranks
         # through FrameParallel.odometry (boundary-descriptor all-gather + pose all-gather over NCCL), one stream ----
         strong = None
+        fps_mode_auto()
         if not args.no_extra:
             from deeppointmap_b200.frames import FrameParallel, shard
             G = args.strong_frames
@@ -639,6 +677,7 @@ def main():
 
         # ---- end-to-end: pinned host frames in, poses out, through the module API ----------
         e2e = None
+        fps_mode_multi()
         if not args.no_e2e:
             stage = [torch.empty((F, 3, n), dtype=torch.float32, device=dev) for _ in range(NS)]
             host_out = [torch.empty((F, _C.REG_STRIDE), dtype=torch.float32).pin_memory() for _ in range(NS)]
@@ -681,6 +720,7 @@ def main():
 
         # ---- batch 1 (BASELINE.json configs[1]/[2]): one frame + one registration at a time, one stream ----
         batch1 = None
+        fps_mode_auto()
         if not args.no_batch1:
             db1 = torch.zeros((2, Cd, S), dtype=torch.float32, device=dev)
             one = [dev_pool[s % nslots][(3 * s) % F:(3 * s) % F + 1].contiguous() for s in range(min(16, 4 * nslots))]
@@ -830,9 +870,11 @@ def main():
                 tot[tag] = round(tot.get(tag, 0.0) + ms, 4)
             return k_, dict(sorted(tot.items(), key=lambda kv: -kv[1]))
 
+        fps_mode_multi()  # the kernels of the timed region
         kern, kern_totals = profile_pass(False)
         prof_total = sum(k[0] for k in kern)
         kern_conc, kern_totals_conc = profile_pass(True) if (NS > 1 and not args.no_extra) else (None, None)
+        fps_mode_auto()
 
     # ---- roofline of the dominant kernel --------------------------------------------------
     peak, peak_src = peaks()
@@ -857,8 +899,8 @@ def main():
         except Exception:
             traffic = None
     sm_total = torch.cuda.get_device_properties(dev).multi_processor_count
-    fps_cluster = F <= int(_C.lib().dpm_fps_cluster_capacity())
-    sms_used = (min(sm_total, 8 * F) if fps_cluster else min(sm_total, F)) if top_tag == "fps" else None
+    fps_cluster = F <= int(_C.lib().dpm_fps_cluster_capacity()) and args.fps_mode in (0, 2)
+    sms_used = (min(sm_total, 8 * F) if fps_cluster else min(sm_total, (F + 1) // 2 if packed else F)) if top_tag == "fps" else None
     conc_launch_ms = None
     if kern_conc:
         for ms_, cnt_, tag_, a_, b_ in kern_conc:
@@ -871,7 +913,9 @@ def main():
                 "dram_frac": (traffic / (per_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "us_per_pick": (1e3 * per_launch_ms / max(1, tb - 1)) if top_tag == "fps" else None,
                 "sms_used": sms_used, "sms_total": sm_total,
-                "fps_mapping": ("cluster of 8 CTAs per cloud" if fps_cluster else "one CTA per cloud") if top_tag == "fps" else None,
+                "fps_mapping": ("cluster of 8 CTAs per cloud" if fps_cluster else
+                                ("two clouds per CTA / SM (packed, dpm_set_fps_mode(3)): us_per_pick is per PAIR of clouds"
+                                 if packed else "one CTA per cloud")) if top_tag == "fps" else None,
                 "launch_ms_concurrent": conc_launch_ms,
                 "note": "`frac` follows SURVEY 8d's streaming model (bytes a brute-force FPS would move) and is NOT an HBM "
                         "utilisation: the exact bucket-pruned FPS touches ~1 % of those bytes and they stay in L2 / shared "
@@ -932,6 +976,9 @@ def main():
                                f"(descriptor match + SVD pose, 256x256 descriptors, k={k_pairs}); {F} frames per GPU per step",
                    "frames_per_gpu_per_step": F, "points_per_frame": n, "global_frames_per_step": world * F,
                    "parallelism": f"frame-parallel x{world}", "streams_per_gpu": NS,
+                   "fps_mode": ("packed: two clouds per SM (dpm_set_fps_mode(3)), chosen for legs of >= 64 steps" if packed else
+                                ("automatic (one SM per cloud at this batch); the packed mapping is kept for legs of >= 64 "
+                                 "steps, see `sustained`" if can_pack else f"dpm_set_fps_mode({args.fps_mode})")),
                    "l2": f"inputs rotate over a {pool_mb:.0f} MiB pool of {nslots} batches per GPU (> 126 MB L2)"},
         "e2e": e2e, "batch1": batch1, "gpu_launches": int(launches), "launches_per_step": launches / K,
         "clocks": clk.summary(), "roofline": roofline, "roofline_tensor": roofline_tensor,

@@ -136,6 +136,7 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
 // latency variants (fps_cluster.cu): one cloud per 8-CTA cluster, chosen by fps_cluster_mode(B)
 constexpr int FPS_BRUTE_CLUSTER_MAX_N = 8192;  // 32 warps x 32 lanes x 8 points in registers
 bool fps_cluster_mode(int B);
+bool fps_packed_mode();  // dpm_set_fps_mode(3): two clouds per SM in the one-SM grid kernel
 bool fps_cluster_mode_small(int B);  // for clouds of <= FPS_BRUTE_CLUSTER_MAX_N points
 int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                             float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);

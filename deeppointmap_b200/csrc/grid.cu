@@ -241,16 +241,30 @@ int grid_build_launch(const float4 *xyz4, int B, int N, const int *len32, float 
 // arg-max (64 points -> bucket, 32 buckets -> warp, 32 warps -> block), not where the points live.
 // Letting untouched warps republish their previous record instead of recomputing it: 4.89 -> 5.36 ms.
 // ---------------------------------------------------------------------------------------
-template <int PPL, int T, int BPT, int D>
-__global__ void __launch_bounds__(T, (T >= 1024 || PPL >= 16) ? 1 : 2)  // narrower teams keep <= 64 registers (the rest of the SM stays free), huge clouds get 128
+// TEAMS > 1: a CTA of TEAMS * T threads holds TEAMS independent teams, each with its own cloud, its own records and its
+// own named barrier -- two 512-thread teams share one SM (the block scheduler would spread two 512-thread CTAs over two
+// SMs and block half of each).
+template <int T, int TEAMS>
+__device__ __forceinline__ void fps_team_sync(int team) {
+    if (TEAMS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(T) : "memory");
+}
+
+template <int PPL, int T, int BPT, int D, int TEAMS = 1>
+__global__ void __launch_bounds__(T * TEAMS, (T * TEAMS >= 1024 || PPL >= 16) ? 1 : 2)  // narrower CTAs keep <= 64 registers (the rest of the SM stays free), huge clouds get 128
 fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int npad,
                 const GridDesc *__restrict__ desc, const float4 *__restrict__ xyz4, int N, int K,
                 int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float4 *__restrict__ new_xyz4,
-                uint8_t *__restrict__ new_pad, int *__restrict__ new_len32) {
+                uint8_t *__restrict__ new_pad, int *__restrict__ new_len32, int nclouds) {
     constexpr int BS = 32 * PPL, W = T / 32;
-    __shared__ unsigned long long skey[2][W];
-    __shared__ float4 sxyz[2][W];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ unsigned long long skey_all[TEAMS][2][W];
+    __shared__ float4 sxyz_all[TEAMS][2][W];
+    const int team = TEAMS == 1 ? 0 : (int)threadIdx.x / T;
+    const int b = blockIdx.x * TEAMS + team;
+    if (b >= nclouds) return;  // a whole team: its named barrier is never used
+    unsigned long long (*skey)[W] = skey_all[team];
+    float4 (*sxyz)[W] = sxyz_all[team];
+    const int tid = TEAMS == 1 ? (int)threadIdx.x : (int)threadIdx.x % T, lane = tid & 31, warp = tid >> 5;
     const int len = desc[b].nvalid;
     const int kn = min(len, K);
     const int nb = (len + BS - 1) / BS;  // <= T * BPT
@@ -314,7 +328,7 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
         if (new_xyz4) new_xyz4[ob] = make_float4(sx, sy, sz, 0.f);
         if (new_pad) new_pad[ob] = 0;
     }
-    __syncthreads();  // M initialised before any bucket is processed (a bucket is only ever touched by its own warp,
+    fps_team_sync<T, TEAMS>(team);  // M initialised before any bucket is processed (a bucket is only ever touched by its own warp,
                       // but keep the prologue and the loop cleanly separated)
 
     int par = 0;
@@ -407,7 +421,7 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
             skey[par][warp] = wmin == 0xffffffffu ? 0ull : (((unsigned long long)wmax << 32) | (unsigned long long)(0xffffffffu - wmin));
             sxyz[par][warp] = make_float4(vx, vy, vz, 0.f);
         }
-        __syncthreads();
+        fps_team_sync<T, TEAMS>(team);
         const unsigned long long kk = lane < W ? skey[par][lane] : 0ull;
         const unsigned hi = (unsigned)(kk >> 32), lo = (unsigned)kk;
         const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
@@ -433,6 +447,8 @@ fps_grid_kernel(const float4 *__restrict__ sorted, float *__restrict__ mind, int
     if (tid == 0 && new_len32) new_len32[b] = kn;
 }
 
+static inline bool p_ok_for_pair(int ppl) { return ppl <= 2; }
+
 int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                     float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st) {
     if (B <= 0 || N <= 0 || K <= 0) return fail(DPM_ERR_SHAPE, "fps: bad shape B=%d N=%d K=%d", B, N, K);
@@ -448,13 +464,16 @@ int fps_grid_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, in
     if (onesm_new && N <= GRID_CLUSTER_MAX_N) return fps_grid_onesm_launch(g, xyz4, B, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, st);
     const int ppl = grid_ppl(N);
     prof_note(N, K);
-#define DPM_FG_ARGS g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, new_pad, new_len32
+#define DPM_FG_ARGS g.sorted, g.mind, g.npad, g.desc, xyz4, N, K, idx64, idx32, new_xyz4, new_pad, new_len32, B
     // team width: 1024 threads own one bucket each; 512 / 256 threads own two / four and leave the rest of the SM's
     // threads and registers to the other streams' kernels (DPM_FPS_T, A/B switch)
     static const int team = getenv("DPM_FPS_T") ? atoi(getenv("DPM_FPS_T")) : 1024;
+    // two 512-thread teams (two clouds) per CTA: dpm_set_fps_mode(3); clouds of <= 65 536 points (no register spills)
+    const bool pair = fps_packed_mode() && p_ok_for_pair(ppl);
 #define DPM_FG_CASE(p)                                                \
     case p:                                                           \
-        if (team == 512) fps_grid_kernel<p, 512, 2, 1><<<B, 512, 0, st>>>(DPM_FG_ARGS); \
+        if (pair) fps_grid_kernel<p, 512, 2, 1, 2><<<(B + 1) / 2, 1024, 0, st>>>(DPM_FG_ARGS); \
+        else if (team == 512) fps_grid_kernel<p, 512, 2, 1><<<B, 512, 0, st>>>(DPM_FG_ARGS); \
         else if (team == 256) fps_grid_kernel<p, 256, 4, 1><<<B, 256, 0, st>>>(DPM_FG_ARGS); \
         else fps_grid_kernel<p, 1024, 1, (p <= 2 ? 2 : 1)><<<B, 1024, 0, st>>>(DPM_FG_ARGS); \
         break;

@@ -36,7 +36,8 @@ def _ws(device, nbytes):
 
 def set_fps_mode(mode: int = 0) -> None:
     """How every FPS of the library maps a cloud onto the chip (`dpm_set_fps_mode`): 0 auto (a cluster of 8 SMs per
-    cloud while the batch is <= 16 clouds, else one SM per cloud), 1 always one SM, 2 always a cluster.  Same picks."""
+    cloud while the batch is <= 16 clouds, else one SM per cloud), 1 always one SM, 2 always a cluster, 3 "packed": two
+    clouds per SM (less SM time, longer latency: for >= 8 streams of 32-frame batches in flight).  Same picks."""
     _C.lib().dpm_set_fps_mode(int(mode))
 
 

@@ -71,7 +71,9 @@ size_t dpm_fps_workspace_bytes(int B, int N, int D, int K);
 /* How a cloud is mapped onto the chip by every FPS in this library (same picks either way): 0 = auto (a
  * cluster of 8 SMs per cloud while all clouds of the call fit the chip at once, B <= dpm_fps_cluster_capacity() -- the latency
  * shape of pipeline/infer.py's batch of 1; one SM per cloud for larger batches, which leaves the other SMs
- * to the kernels of concurrent streams), 1 = always one SM per cloud, 2 = always a cluster.  Process-wide. */
+ * to the kernels of concurrent streams), 1 = always one SM per cloud, 2 = always a cluster, 3 = "packed": TWO clouds
+ * per SM in the one-SM kernel (clouds of <= 65 536 points) -- 22 % less SM time per batch at 1.55x the latency of its
+ * FPS, for callers that keep >= 8 streams of batches in flight.  Process-wide. */
 void dpm_set_fps_mode(int mode);
 /* clouds per call up to which mode 0 takes the cluster mapping: the number of 8-CTA clusters of the largest FPS
  * kernel the current device can hold at once (cudaOccupancyMaxActiveClusters) */

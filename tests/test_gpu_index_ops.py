@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=[1, 2], ids=["one-sm", "cluster"])
+@pytest.fixture(params=[1, 2, 3], ids=["one-sm", "cluster", "packed"])
 def fps_mode(request):
-    """every FPS test runs on both mappings: one CTA per cloud (grid.cu / fps.cu) and an 8-CTA cluster per cloud
-    (fps_cluster.cu)"""
+    """every FPS test runs on all three mappings: one CTA per cloud (grid.cu / fps.cu), an 8-CTA cluster per cloud
+    (fps_cluster.cu) and two clouds per CTA (two teams with their own named barriers, grid.cu)"""
     ops.set_fps_mode(request.param)
     yield request.param
     ops.set_fps_mode(0)
@@ -58,7 +58,7 @@ def test_fps_duplicates_first_maximum(fps_mode):
 
 
 def test_fps_batch_of_full_frames(fps_mode):
-    pts = torch.stack([_cloud("kitti", s, 65536) for s in range(3)])
+    pts = torch.stack([_cloud("kitti", s, 65536) for s in range(3)])  # odd batch: the packed mapping's last team idles
     want = IO.fps(pts, None, 4096)
     _, got = ops.sample_farthest_points(pts.to(DEV), K=4096)
     assert torch.equal(got.cpu(), want)
