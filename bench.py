@@ -48,6 +48,8 @@ def parse():
                     help="dpm_set_fps_mode for the multi-stream legs (headline, sustained, e2e, kernel profile): 3 = packed, two "
                          "clouds per SM (less SM time per batch, longer FPS latency: pays with >= 8 streams in flight); 0 = the "
                          "library's automatic choice.  The one-stream legs (batch1, strong, caller sizes) always run on 0")
+    ap.add_argument("--pack-min-steps", type=int, default=64,
+                    help="steps from which a multi-stream leg takes the packed FPS mapping (profiling runs pass 1)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -519,7 +521,7 @@ def main():
     # pipeline long enough to leave the lock-step start behind (measured: 7480 against 7240 frames/s at 200 steps, but
     # 6910 against 7160 at 20 steps).  So a leg of >= 64 steps runs packed on 8 streams, a shorter one on the library's
     # automatic mapping with 6 / 5 / 4 streams.
-    PACK_MIN_STEPS = 64
+    PACK_MIN_STEPS = args.pack_min_steps
     can_pack = args.fps_mode == 3 and F > int(_C.lib().dpm_fps_cluster_capacity())
 
     def leg_config(nsteps, flexible=False):
