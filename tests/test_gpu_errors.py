@@ -28,9 +28,13 @@ def test_error_codes_and_messages():
     assert rc == -1 and "D=2" in msg
     rc, msg = _err(lib.dpm_fps_f32(x.data_ptr(), 4, 8, 3, None, 4, idx.data_ptr(), None, ws.data_ptr(), 16, st))
     assert rc == -3 and "workspace" in msg
-    rc, msg = _err(lib.dpm_knn_f32(x.data_ptr(), 3, x.data_ptr(), 3, 4, 8, 8, None, None, 64, idx.data_ptr(), None, ws.data_ptr(),
+    rc, msg = _err(lib.dpm_knn_f32(x.data_ptr(), 3, x.data_ptr(), 3, 4, 8, 8, None, None, 0, idx.data_ptr(), None, ws.data_ptr(),
                                    ws.numel(), st))
-    assert rc == -2 and "K=64" in msg
+    assert rc == -1 and "K=0" in msg
+    # DPM_ERR_UNSUPPORTED: a leading dimension the attention kernels cannot take (checked before any launch)
+    rc, msg = _err(lib.dpm_attention_f32(x.data_ptr(), 3, x.data_ptr(), 3, x.data_ptr(), 3, x.data_ptr(), 3, idx.data_ptr(), 1, 8,
+                                         1, st))
+    assert rc == -2 and "multiples of 4" in msg
     rc, msg = _err(lib.dpm_information_matrix_f32(x.data_ptr(), 0, x.data_ptr(), 8, x.data_ptr(), 1.0, x.data_ptr(), None,
                                                   ws.data_ptr(), ws.numel(), st))
     assert rc == -1
