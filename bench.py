@@ -897,7 +897,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(top_tag)
+            tj = json.load(open(tp))
+            traffic = tj.get("fps_packed" if (top_tag == "fps" and packed) else top_tag, tj.get(top_tag))
         except Exception:
             traffic = None
     sm_total = torch.cuda.get_device_properties(dev).multi_processor_count
