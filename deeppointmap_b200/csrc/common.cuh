@@ -182,7 +182,7 @@ int linear_batched_launch(const float *X, int ldx, long long sX, const float *W,
                           int N, int K, int nbatch, int act, cudaStream_t st);
 bool linear_ln_tc_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res,
                          int ldres, const float *gamma, const float *beta, const float *post, int ldpost, float *Y,
-                         int ldy, int M, int N, int K, int act, cudaStream_t st, int *rc);
+                         int ldy, int M, int N, int K, int act, cudaStream_t st, int *rc, float *tmp = nullptr);
 // Y = act(LayerNorm_N(X W^T + bias + res) * gamma + beta + post): fused when eligible, else linear + layernorm via
 // the scratch buffer `tmp` (M x N, may be Y itself when Y does not alias res / post)
 int linear_ln_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res, int ldres,

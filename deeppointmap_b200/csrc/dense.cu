@@ -400,7 +400,7 @@ int linear_ln_launch(const float *X, int ldx, const float *W, int ldw, const flo
                      const float *gamma, const float *beta, const float *post, int ldpost, float *tmp, float *Y, int ldy,
                      int M, int N, int K, int act, cudaStream_t st, int tmp_copies) {
     int rc = DPM_OK;
-    if (linear_ln_tc_launch(X, ldx, W, ldw, bias, res, ldres, gamma, beta, post, ldpost, Y, ldy, M, N, K, act, st, &rc))
+    if (linear_ln_tc_launch(X, ldx, W, ldw, bias, res, ldres, gamma, beta, post, ldpost, Y, ldy, M, N, K, act, st, &rc, tmp))
         return rc;
     int ks = tmp_copies;
     while (ks > 1 && (K % (ks * 32) != 0)) --ks;

@@ -131,6 +131,22 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
     else asm volatile("bar.sync 4, 64;" ::: "memory");
 }
 
+// LayerNorm arithmetic shared by the fused epilogue and ln_fused_order_kernel (the few-rows path): written with explicit
+// round-to-nearest intrinsics so that both kernels contract nothing differently -- the same row gives the same bits
+// whichever path its batch size selects.
+__device__ __forceinline__ float ln_sq4(const float4 o, float mean) {
+    const float dx = __fsub_rn(o.x, mean), dy = __fsub_rn(o.y, mean), dz = __fsub_rn(o.z, mean), dw = __fsub_rn(o.w, mean);
+    return __fadd_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)), __fmaf_rn(dz, dz, __fmul_rn(dw, dw)));
+}
+__device__ __forceinline__ float ln_sum4(const float4 o) { return __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w)); }
+__device__ __forceinline__ float ln_out(float o, float mean, float rstd, float g, float b, float p) {
+    return __fadd_rn(__fmaf_rn(__fmul_rn(__fsub_rn(o, mean), rstd), g, b), p);
+}
+__device__ __forceinline__ float ln_mean(float s0, float s1, int N) { return __fdiv_rn(__fadd_rn(s0, s1), (float)N); }
+__device__ __forceinline__ float ln_rstd(float q0, float q1, int N) {
+    return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(__fadd_rn(q0, q1), (float)N), 1e-5f)));
+}
+
 struct LnArgs {  // fused LayerNorm epilogue: Y = act(LN_N(acc + bias + res) * gamma + beta + post)
     const float *gamma, *beta, *post;
     int ldpost;
@@ -266,7 +282,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
                     o.x += bb.x + r4.x; o.y += bb.y + r4.y; o.z += bb.z + r4.z; o.w += bb.w + r4.w;
                     if (!cok) o = make_float4(0.f, 0.f, 0.f, 0.f);
                     *reinterpret_cast<float4 *>(tile + lr * TS + col) = o;
-                    sum[i] += (o.x + o.y) + (o.z + o.w);
+                    sum[i] = __fadd_rn(sum[i], ln_sum4(o));
                 }
             }
             // ---- mean ----
@@ -281,7 +297,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int lr = quarter * 32 + i * 4 + rsub;
-                mean[i] = (stat[lr] + stat[128 + lr]) / (float)N;
+                mean[i] = ln_mean(stat[lr], stat[128 + lr], N);
                 sum[i] = 0.f;
             }
             // ---- variance ----
@@ -293,8 +309,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 o = *reinterpret_cast<const float4 *>(tile + (quarter * 32 + i * 4 + rsub) * TS + col);
-                        const float dx = o.x - mean[i], dy = o.y - mean[i], dz = o.z - mean[i], dw = o.w - mean[i];
-                        sum[i] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                        sum[i] = __fadd_rn(sum[i], ln_sq4(o, mean[i]));
                     }
                 }
             }
@@ -309,7 +324,7 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int lr = quarter * 32 + i * 4 + rsub;
-                rstd[i] = 1.0f / sqrtf((stat[256 + lr] + stat[384 + lr]) / (float)N + 1e-5f);
+                rstd[i] = ln_rstd(stat[256 + lr], stat[384 + lr], N);
             }
             // ---- normalise, affine, post-add, activation, store ----
 #pragma unroll 1
@@ -330,10 +345,10 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
                 for (int i = 0; i < 8; ++i) {
                     const int lr = quarter * 32 + i * 4 + rsub, row = m0 + lr;
                     float4 o = *reinterpret_cast<const float4 *>(tile + lr * TS + col);
-                    o.x = (o.x - mean[i]) * rstd[i] * g4.x + b4.x + p4[i].x;
-                    o.y = (o.y - mean[i]) * rstd[i] * g4.y + b4.y + p4[i].y;
-                    o.z = (o.z - mean[i]) * rstd[i] * g4.z + b4.z + p4[i].z;
-                    o.w = (o.w - mean[i]) * rstd[i] * g4.w + b4.w + p4[i].w;
+                    o.x = ln_out(o.x, mean[i], rstd[i], g4.x, b4.x, p4[i].x);
+                    o.y = ln_out(o.y, mean[i], rstd[i], g4.y, b4.y, p4[i].y);
+                    o.z = ln_out(o.z, mean[i], rstd[i], g4.z, b4.z, p4[i].z);
+                    o.w = ln_out(o.w, mean[i], rstd[i], g4.w, b4.w, p4[i].w);
                     if (act == DPM_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     if (row < M) *reinterpret_cast<float4 *>(Y + (size_t)row * ldy + col) = o;
                 }
@@ -376,8 +391,9 @@ linear_tc_kernel(const float *__restrict__ X, int ldx, const float *__restrict__
                     const int row = m0 + quarter * 32 + r, cc = n0 + cb + lane;
                     if (row < M && cc < N) {
                         float o = tb[r * TLD + lane];
-                        if (bias) o += bias[cc];
-                        if (res) o += res[(size_t)row * ldres + cc];
+                        float add = bias ? bias[cc] : 0.f;  // acc + (bias + res): the association of the vector path
+                        if (res) add += res[(size_t)row * ldres + cc];
+                        o += add;
                         if (act == DPM_ACT_RELU) o = fmaxf(o, 0.f);
                         Y[(size_t)row * ldy + cc] = o;
                     }
@@ -498,14 +514,96 @@ static int launch_s(const float *X, int ldx, long long sX, const float *W, int l
     return DPM_OK;
 }
 
+// LayerNorm of rows that a NARROW-tile GEMM left in global memory (acc + bias + res already added), in exactly the
+// summation order of the fused epilogue of a 128 x BN tile: 8 lanes per row, 4 columns per lane and 32-column chunk,
+// the two column halves of the tile summed separately (they are two warps there) and then added.  Same bits as the
+// fused kernel for the same row.
+__global__ void __launch_bounds__(256)
+ln_fused_order_kernel(const float *T, int ldt, const float *__restrict__ gamma, const float *__restrict__ beta,
+                      const float *post, int ldpost, float *Y, int ldy, int M, int N, int BN, int act) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = (blockIdx.x * 8 + warp) * 4 + (lane >> 3), c4 = (lane & 7) * 4;
+    const bool rok = row < M;
+    const int CHALF = BN >= 64 ? BN / 2 : BN;
+    const float *t = T + (size_t)(rok ? row : 0) * ldt;
+    float s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int cbeg = h * CHALF, cend = BN >= 64 ? (h + 1) * CHALF : (h == 0 ? BN : 0);
+        for (int cb = cbeg; cb < cend; cb += 32) {
+            if (cb >= N) break;
+            const int col = cb + c4;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rok && col < N) o = *reinterpret_cast<const float4 *>(t + col);
+            s[h] = __fadd_rn(s[h], ln_sum4(o));
+        }
+        s[h] += __shfl_xor_sync(0xffffffffu, s[h], 1);
+        s[h] += __shfl_xor_sync(0xffffffffu, s[h], 2);
+        s[h] += __shfl_xor_sync(0xffffffffu, s[h], 4);
+    }
+    const float mean = ln_mean(s[0], s[1], N);
+    float q[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int cbeg = h * CHALF, cend = BN >= 64 ? (h + 1) * CHALF : (h == 0 ? BN : 0);
+        for (int cb = cbeg; cb < cend; cb += 32) {
+            if (cb >= N) break;
+            const int col = cb + c4;
+            if (col < N) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rok) o = *reinterpret_cast<const float4 *>(t + col);
+                q[h] = __fadd_rn(q[h], ln_sq4(o, mean));
+            }
+        }
+        q[h] += __shfl_xor_sync(0xffffffffu, q[h], 1);
+        q[h] += __shfl_xor_sync(0xffffffffu, q[h], 2);
+        q[h] += __shfl_xor_sync(0xffffffffu, q[h], 4);
+    }
+    const float rstd = ln_rstd(q[0], q[1], N);
+    if (!rok) return;
+    for (int cb = 0; cb < N; cb += 32) {
+        const int col = cb + c4;
+        if (col >= N) continue;
+        const float4 g4 = __ldg(reinterpret_cast<const float4 *>(gamma + col));
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(beta + col));
+        float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (post) p4 = *reinterpret_cast<const float4 *>(post + (size_t)row * ldpost + col);
+        float4 o = *reinterpret_cast<const float4 *>(t + col);
+        o.x = ln_out(o.x, mean, rstd, g4.x, b4.x, p4.x);
+        o.y = ln_out(o.y, mean, rstd, g4.y, b4.y, p4.y);
+        o.z = ln_out(o.z, mean, rstd, g4.z, b4.z, p4.z);
+        o.w = ln_out(o.w, mean, rstd, g4.w, b4.w, p4.w);
+        if (act == DPM_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4 *>(Y + (size_t)row * ldy + col) = o;
+    }
+}
+
 }  // namespace tc
+
+// FEW ROWS (one frame per call: 512 decoder tokens, 16 ... 1024 points of the deeper encoder stages): a 128 x 256 tile
+// leaves 1-8 CTAs on the chip, each walking all K blocks with 12 wide MMAs per block and, when LayerNorm rides in the
+// epilogue, parking the whole 128 x 256 tile in shared memory -- 20-26 us per layer, pure latency.  Narrow column tiles
+// spread the same rows over 4x the CTAs with a quarter of the MMA time each; LayerNorm then runs as its own (small) launch.
+// DPM_TC_SMALL_M: rows up to which the narrow tiles are taken (0 = never); DPM_TC_SMALL_BN: their width (32 / 64 / 128).
+static int small_m_rows() {
+    static const int v = getenv("DPM_TC_SMALL_M") ? atoi(getenv("DPM_TC_SMALL_M")) : 1024;
+    return v;
+}
+static int small_m_bn() {
+    static const int v = getenv("DPM_TC_SMALL_BN") ? atoi(getenv("DPM_TC_SMALL_BN")) : 64;
+    return (v == 32 || v == 64 || v == 128) ? v : 64;
+}
+
+int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int ldw, long long sW, const float *bias,
+                     const float *res, int ldres, float *Y, int ldy, long long sY, int M, int N, int K, int nbatch,
+                     int act, cudaStream_t st);
 
 // Y = act(LayerNorm_N(X W^T + bias + res) * gamma + beta + post) in ONE launch when the row fits one column
 // tile (N <= 256) and the weights were pre-split for this call; false = not eligible (caller runs the two
 // kernels).  Y may alias res and / or post (a CTA reads its own rows before it writes them).
 bool linear_ln_tc_launch(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *res,
                          int ldres, const float *gamma, const float *beta, const float *post, int ldpost, float *Y,
-                         int ldy, int M, int N, int K, int act, cudaStream_t st, int *rc) {
+                         int ldy, int M, int N, int K, int act, cudaStream_t st, int *rc, float *tmp) {
     static const bool off = getenv("DPM_NO_LN_FUSION") != nullptr;
     if (off || N > 256 || (N & 3) || M < 1 || (K & 3) || (ldx & 3) || (((uintptr_t)X) & 15)) return false;
     if ((ldy & 3) || (((uintptr_t)Y) & 15) || (bias && (((uintptr_t)bias) & 15)) || (((uintptr_t)gamma) & 15) ||
@@ -515,6 +613,17 @@ bool linear_ln_tc_launch(const float *X, int ldx, const float *W, int ldw, const
     if (post && ((ldpost & 3) || (((uintptr_t)post) & 15))) return false;
     const float *Ws = split_lookup(W, N, K, ldw);
     if (!Ws || getenv("DPM_NO_TC")) return false;
+    if (M <= small_m_rows() && N > small_m_bn() && tmp && tmp != X && tmp != res && (((uintptr_t)tmp) & 15) == 0) {
+        // few rows: narrow column tiles (4x the CTAs, a quarter of the MMA time each) leave acc + bias + res in `tmp`;
+        // the LayerNorm is a second, small launch that sums in the fused epilogue's order -- same bits either way
+        *rc = linear_tc_launch(X, ldx, 0, W, ldw, 0, bias, res, ldres, tmp, N, 0, M, N, K, 1, DPM_ACT_NONE, st);
+        if (*rc != DPM_OK) return true;
+        const int BN = N <= 128 ? 128 : 256;
+        tc::ln_fused_order_kernel<<<(M + 31) / 32, 256, 0, st>>>(tmp, N, gamma, beta, post, ldpost, Y, ldy, M, N, BN, act);
+        count_launch("layernorm", st);
+        *rc = cudaGetLastError() == cudaSuccess ? DPM_OK : fail(DPM_ERR_CUDA, "layernorm launch failed");
+        return true;
+    }
     prof_note((long long)M, (long long)N * K);
     const tc::LnArgs ln{gamma, beta, post, ldpost};
     const long long lo = (long long)N * ((K + 31) & ~31);
@@ -546,6 +655,12 @@ int linear_tc_launch(const float *X, int ldx, long long sX, const float *W, int 
     if (Ws) {
         const long long lo = (long long)N * ((K + 31) & ~31);
 #define DPM_TC_ARGS X, ldx, sX, Ws, K, 0, bias, res, ldres, Y, ldy, sY, M, N, K, nbatch, act, lo, st
+        if (M <= small_m_rows() && N > small_m_bn()) {
+            const int bn = small_m_bn();
+            if (bn == 32) return tc::launch_t<32, 4, true>(DPM_TC_ARGS);
+            if (bn == 64) return tc::launch_t<64, 4, true>(DPM_TC_ARGS);
+            return tc::launch_t<128, 3, true>(DPM_TC_ARGS);
+        }
         if (N <= 32) return tc::launch_t<32, 4, true>(DPM_TC_ARGS);
         if (N <= 64) return tc::launch_t<64, 4, true>(DPM_TC_ARGS);
         if (N <= 128) return tc::launch_t<128, 3, true>(DPM_TC_ARGS);

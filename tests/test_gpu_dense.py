@@ -92,6 +92,49 @@ def test_linear_layernorm_fused(M, N, K, mode):
     assert rel_err(Y, ref) < 2e-5
 
 
+@pytest.mark.parametrize("N,K", [(256, 256), (128, 512), (96, 64), (200, 128), (768, 256)])
+def test_few_rows_take_narrow_tiles_with_the_same_bits(N, K):
+    """One frame per call leaves 1-8 row tiles per layer: those calls take narrow column tiles (4x the CTAs) and, for
+    LayerNorm layers, a separate LayerNorm launch that sums in the fused epilogue's order (gemm_tc.cu).  Batch
+    independence must survive that: the first 512 rows of a 4096-row call (wide tiles, fused LayerNorm) and a 512-row call
+    of their own (narrow tiles) agree BIT FOR BIT, with and without residual / post-add."""
+    g = torch.Generator().manual_seed(7 * N + K)
+    M, m = 4096, 512
+    X, W = torch.randn(M, K, generator=g).to(DEV), (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b, gam, bet = (torch.randn(N, generator=g).to(DEV) for _ in range(3))
+    res, post = torch.randn(M, N, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    lib = _C.lib()
+    st = _C.stream_ptr()
+
+    def lin(rows):
+        nb = lib.dpm_linear_workspace_bytes(N, K)
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        Y = torch.empty(rows, N, device=DEV)
+        _C.check(lib.dpm_linear_ws_f32(X.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), res.data_ptr(), N, Y.data_ptr(), N,
+                                       rows, N, K, _C.ACT_RELU, ws.data_ptr(), nb, st))
+        return Y
+
+    assert torch.equal(lin(M)[:m], lin(m))
+    if N > 256:
+        return
+
+    def lin_ln(rows, with_res):
+        nb = lib.dpm_linear_ln_workspace_bytes(rows, N, K)
+        ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+        Y = torch.empty(rows, N, device=DEV)
+        _C.check(lib.dpm_linear_ln_ws_f32(X.data_ptr(), K, W.data_ptr(), K, b.data_ptr(), res.data_ptr() if with_res else None,
+                                          N, gam.data_ptr(), bet.data_ptr(), post.data_ptr() if with_res else None, N,
+                                          Y.data_ptr(), N, rows, N, K, _C.ACT_RELU, ws.data_ptr(), nb, st))
+        return Y
+
+    for with_res in (False, True):
+        wide, narrow = lin_ln(M, with_res), lin_ln(m, with_res)
+        assert torch.equal(wide[:m], narrow)
+        y = X[:m].double() @ W.double().T + b.double() + (res[:m].double() if with_res else 0)
+        ref = F.relu(F.layer_norm(y, (N,), gam.double(), bet.double(), 1e-5) + (post[:m].double() if with_res else 0))
+        assert rel_err(narrow, ref) < 2e-5
+
+
 @pytest.mark.parametrize("M,C", [(1, 32), (1000, 32), (77, 128), (16, 2048), (4096, 256), (5, 48)])
 def test_layernorm(M, C):
     g = torch.Generator().manual_seed(C)
