@@ -526,55 +526,61 @@ ln_fused_order_kernel(const float *T, int ldt, const float *__restrict__ gamma, 
     const bool rok = row < M;
     const int CHALF = BN >= 64 ? BN / 2 : BN;
     const float *t = T + (size_t)(rok ? row : 0) * ldt;
-    float s[2] = {0.f, 0.f};
+    // the lane's 4 columns of every 32-column chunk (N <= 256: at most 8 chunks), all loads in flight together
+    float4 o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int col = c * 32 + c4;
+        o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && col < N) o[c] = *reinterpret_cast<const float4 *>(t + col);
+    }
+    float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int cb = c * 32;
+        if (cb < N && cb < BN) {                       // the fused loop: cb in [half begin, half end), break at cb >= N
+            const int h = (BN >= 64 && cb >= CHALF) ? 1 : 0;
+            s[h] = __fadd_rn(s[h], ln_sum4(o[c]));
+        }
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int cbeg = h * CHALF, cend = BN >= 64 ? (h + 1) * CHALF : (h == 0 ? BN : 0);
-        for (int cb = cbeg; cb < cend; cb += 32) {
-            if (cb >= N) break;
-            const int col = cb + c4;
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rok && col < N) o = *reinterpret_cast<const float4 *>(t + col);
-            s[h] = __fadd_rn(s[h], ln_sum4(o));
-        }
         s[h] += __shfl_xor_sync(0xffffffffu, s[h], 1);
         s[h] += __shfl_xor_sync(0xffffffffu, s[h], 2);
         s[h] += __shfl_xor_sync(0xffffffffu, s[h], 4);
     }
     const float mean = ln_mean(s[0], s[1], N);
-    float q[2] = {0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int cb = c * 32;
+        if (cb < N && cb < BN && cb + c4 < N) {
+            const int h = (BN >= 64 && cb >= CHALF) ? 1 : 0;
+            q[h] = __fadd_rn(q[h], ln_sq4(o[c], mean));
+        }
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int cbeg = h * CHALF, cend = BN >= 64 ? (h + 1) * CHALF : (h == 0 ? BN : 0);
-        for (int cb = cbeg; cb < cend; cb += 32) {
-            if (cb >= N) break;
-            const int col = cb + c4;
-            if (col < N) {
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rok) o = *reinterpret_cast<const float4 *>(t + col);
-                q[h] = __fadd_rn(q[h], ln_sq4(o, mean));
-            }
-        }
         q[h] += __shfl_xor_sync(0xffffffffu, q[h], 1);
         q[h] += __shfl_xor_sync(0xffffffffu, q[h], 2);
         q[h] += __shfl_xor_sync(0xffffffffu, q[h], 4);
     }
     const float rstd = ln_rstd(q[0], q[1], N);
     if (!rok) return;
-    for (int cb = 0; cb < N; cb += 32) {
-        const int col = cb + c4;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int col = c * 32 + c4;
         if (col >= N) continue;
         const float4 g4 = __ldg(reinterpret_cast<const float4 *>(gamma + col));
         const float4 b4 = __ldg(reinterpret_cast<const float4 *>(beta + col));
         float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (post) p4 = *reinterpret_cast<const float4 *>(post + (size_t)row * ldpost + col);
-        float4 o = *reinterpret_cast<const float4 *>(t + col);
-        o.x = ln_out(o.x, mean, rstd, g4.x, b4.x, p4.x);
-        o.y = ln_out(o.y, mean, rstd, g4.y, b4.y, p4.y);
-        o.z = ln_out(o.z, mean, rstd, g4.z, b4.z, p4.z);
-        o.w = ln_out(o.w, mean, rstd, g4.w, b4.w, p4.w);
-        if (act == DPM_ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        *reinterpret_cast<float4 *>(Y + (size_t)row * ldy + col) = o;
+        float4 r;
+        r.x = ln_out(o[c].x, mean, rstd, g4.x, b4.x, p4.x);
+        r.y = ln_out(o[c].y, mean, rstd, g4.y, b4.y, p4.y);
+        r.z = ln_out(o[c].z, mean, rstd, g4.z, b4.z, p4.z);
+        r.w = ln_out(o[c].w, mean, rstd, g4.w, b4.w, p4.w);
+        if (act == DPM_ACT_RELU) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+        *reinterpret_cast<float4 *>(Y + (size_t)row * ldy + col) = r;
     }
 }
 
