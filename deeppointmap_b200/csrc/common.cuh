@@ -138,6 +138,8 @@ constexpr int FPS_BRUTE_CLUSTER_MAX_N = 8192;  // 32 warps x 32 lanes x 8 points
 bool fps_cluster_mode(int B);
 bool fps_packed_mode();  // dpm_set_fps_mode(3): two clouds per SM in the one-SM grid kernel
 bool fps_cluster_mode_small(int B);  // for clouds of <= FPS_BRUTE_CLUSTER_MAX_N points
+// smallest cloud that takes the pruned (grid) FPS; smaller ones stay in registers (fps.cu)
+int fps_grid_min_n();
 int fps_grid_cluster_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,
                             float4 *new_xyz4, uint8_t *new_pad, int *new_len32, cudaStream_t st);
 int fps_grid_onesm_launch(const GridWs &g, const float4 *xyz4, int B, int N, int K, int64_t *idx64, int32_t *idx32,

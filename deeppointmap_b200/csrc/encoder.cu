@@ -265,7 +265,7 @@ static int encoder_run(const dpm_encoder_desc *d, const float *const *w, int n_w
                 // the pruned FPS only pays from ~2048 points on; with a cluster per cloud (few clouds, fps_cluster.cu) the
                 // register-resident brute-force kernel wins up to 8192 points
                 const bool brute = src.n <= FPS_BRUTE_CLUSTER_MAX_N && fps_cluster_mode_small(B);
-                if (src.has_grid && src.n >= GRID_MIN_N && !brute)
+                if (src.has_grid && src.n >= fps_grid_min_n() && !brute)
                     DPM_TRY(fps_grid_launch(src.grid, src.xyz, B, src.n, S, trace_fps ? trace_fps + fps_off : nullptr, nullptr,
                                             dst.xyz, dst.pad, dst.len, sst));
                 else

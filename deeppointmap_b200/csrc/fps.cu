@@ -12,6 +12,8 @@
 //      memory of EVERY CTA of the cluster (DSMEM stores), double-buffered by step parity;
 //   4. one cluster barrier; every warp reduces the CS*16 records locally and knows the pick
 //      and its coordinates -- no second barrier, no global-memory round trip.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dpm {
@@ -205,12 +207,25 @@ static void fps_pick(int N, int B, int *P, int *CS) {
     int p = 1;
     while (p < 16 && (long long)cs * FPS_T * p < N) p *= 2;
     const int sms = device_sm_count();
-    while (cs < 8 && p > 2 && (long long)B * cs * 2 <= sms) {
+    // Widening used to pay when a batch left SMs idle; batches that reach this kernel are throughput work now (<= 15 clouds
+    // take the cluster kernels of fps_cluster.cu), and with several streams in flight SM time is what counts: clusters of
+    // 4 for the 4096-point level cost 7 % of the 32-frame step (6890 against 7480 frames/s).  DPM_FPS_REG_MAXCS=8 restores it.
+    static const int maxcs = getenv("DPM_FPS_REG_MAXCS") ? atoi(getenv("DPM_FPS_REG_MAXCS")) : 1;
+    while (cs < maxcs && p > 2 && (long long)B * cs * 2 <= sms) {
         cs *= 2;
         p /= 2;
     }
     *P = p;
     *CS = cs;
+}
+
+// Clouds of <= 8192 points stay in registers (512 threads x <= 16 points, 80 registers at 8 points: half an SM's threads
+// and 60 % of its registers, against a whole SM for the pruned kernel, whose bucket bookkeeping only pays from ~10 000
+// points on): level 1 of the encoder (4096 -> 1024) 7130 -> 7240 frames/s in the driver's 20-step run, 7480 -> 7535 at
+// 200 steps.  DPM_FPS_GRID_MIN_N=2048 restores the old split.
+int fps_grid_min_n() {
+    static const int v = getenv("DPM_FPS_GRID_MIN_N") ? atoi(getenv("DPM_FPS_GRID_MIN_N")) : FPS_BRUTE_CLUSTER_MAX_N + 1;
+    return v < GRID_MIN_N ? GRID_MIN_N : v;
 }
 
 int fps_launch(const float4 *xyz4, int B, int N, const int *len32, int K, int64_t *idx64, int32_t *idx32,
@@ -297,7 +312,7 @@ extern "C" int dpm_fps_f32(const float *points, int B, int N, int D, const int64
     DPM_TRY(pack_xyz4_launch(points, B, N, D, xyz4, st));
     DPM_TRY(lengths_to_i32_launch(lengths, B, N, len32, st));
     const bool brute = N <= FPS_BRUTE_CLUSTER_MAX_N && fps_cluster_mode_small(B);
-    if (N >= GRID_MIN_N && N <= GRID_MAX_N && !brute) {
+    if (N >= fps_grid_min_n() && N <= GRID_MAX_N && !brute) {
         GridWs g;
         if (!grid_ws_carve(a, B, N, &g)) return fail(DPM_ERR_WORKSPACE, "fps: workspace too small");
         DPM_TRY(grid_build_launch(xyz4, B, N, len32, 0.f, g, st));

@@ -223,11 +223,11 @@ def test_fps_grid_ties_on_lattice(n, k, fps_mode):
     assert torch.equal(got.cpu(), want)
 
 
-def test_fps_grid_lengths_and_degenerate_clouds(fps_mode):
-    n, k = 6000, 900
+@pytest.mark.parametrize("n,k", [(6000, 900), (12000, 700)])  # register-resident kernel / pruned (grid) kernel
+def test_fps_grid_lengths_and_degenerate_clouds(n, k, fps_mode):
     pts = torch.stack([_cloud("kitti", 1, n), _cloud("cube", 2, n), torch.zeros(n, 3), _cloud("kitti", 3, n),
                        _cloud("cube", 4, n) * torch.tensor([1.0, 0.0, 0.0])])  # identical points; a line
-    lengths = torch.tensor([6000, 2500, 6000, 1, 6000])
+    lengths = torch.tensor([n, 2500, n, 1, n])
     want = IO.fps(pts, lengths, k)
     _, got = ops.sample_farthest_points(pts.to(DEV), lengths.to(DEV), K=k)
     assert torch.equal(got.cpu(), want)
