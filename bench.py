@@ -681,31 +681,61 @@ def main():
         e2e = None
         fps_mode_multi()
         if not args.no_e2e:
-            stage = [torch.empty((F, 3, n), dtype=torch.float32, device=dev) for _ in range(NS)]
-            host_out = [torch.empty((F, _C.REG_STRIDE), dtype=torch.float32).pin_memory() for _ in range(NS)]
-            done = [None] * NS
+            # two steps in flight per stream (double-buffered staging / result buffers): the host reads the poses of step
+            # i - 2 NS while step i - NS still runs, so a stream never idles waiting for the host to notice its last step
+            DEPTH = 2
+            stage = [[torch.empty((F, 3, n), dtype=torch.float32, device=dev) for _ in range(DEPTH)] for _ in range(NS)]
+            host_out = [[torch.empty((F, _C.REG_STRIDE), dtype=torch.float32).pin_memory() for _ in range(DEPTH)] for _ in range(NS)]
+            done = [[None] * DEPTH for _ in range(NS)]
+            turn = [0] * NS
             poses_seen = [0]
 
+            h2d = torch.cuda.Stream(device=dev)      # input prefetch: the copy of a stream's NEXT step runs under its current one
+            ready = [[None] * DEPTH for _ in range(NS)]  # (step index, event) of a prefetched input
+            e2e_end = [0]                                # one past the last step of the current run: nothing is prefetched beyond it
+
             def e2e_step(i, q):
-                if done[q] is not None:      # the consumer reads step i-NS's poses before its buffers are reused
-                    done[q].synchronize()
-                    poses_seen[0] += int(host_out[q].shape[0])
-                stage[q].copy_(host_pool[i % nslots], non_blocking=True)
-                result, _ = step(stage[q], q)
-                host_out[q].copy_(result, non_blocking=True)
-                done[q] = torch.cuda.Event()
-                done[q].record()
+                j = turn[q]
+                turn[q] = (j + 1) % DEPTH
+                if done[q][j] is not None:   # the consumer reads step i - DEPTH * NS's poses before its buffers are reused
+                    done[q][j].synchronize()
+                    poses_seen[0] += int(host_out[q][j].shape[0])
+                cur = torch.cuda.current_stream()
+                if ready[q][j] is not None and ready[q][j][0] == i:
+                    cur.wait_event(ready[q][j][1])
+                else:
+                    stage[q][j].copy_(host_pool[i % nslots], non_blocking=True)
+                ready[q][j] = None
+                result, _ = step(stage[q][j], q)
+                host_out[q][j].copy_(result, non_blocking=True)
+                done[q][j] = torch.cuda.Event()
+                done[q][j].record()
+                # prefetch the input of this stream's next step into the other staging buffer, once its last user is done
+                jn, nxt = turn[q], i + NS
+                if nxt < e2e_end[0]:
+                    if done[q][jn] is not None:
+                        h2d.wait_event(done[q][jn])
+                    with torch.cuda.stream(h2d):
+                        stage[q][jn].copy_(host_pool[nxt % nslots], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record()
+                    ready[q][jn] = (nxt, ev)
 
             def drain():
+                h2d.synchronize()
                 for q in range(NS):
-                    if done[q] is not None:
-                        done[q].synchronize()
-                        poses_seen[0] += int(host_out[q].shape[0])
-                        done[q] = None
+                    for j in range(DEPTH):
+                        ready[q][j] = None
+                        if done[q][j] is not None:
+                            done[q][j].synchronize()
+                            poses_seen[0] += int(host_out[q][j].shape[0])
+                            done[q][j] = None
 
+            e2e_end[0] = max(3, W // 2)
             run_steps(max(3, W // 2), 0, e2e_step)
             drain()
             barrier()
+            e2e_end[0] = W + K
             t0 = time.perf_counter()
             run_steps(K, W, e2e_step)
             drain()
@@ -718,7 +748,8 @@ def main():
                    "d2h_bytes_per_step": F * _C.REG_STRIDE * 4, "ms_per_step": 1e3 * float(tt.item()) / K,
                    "timing": "host wall clock around K steps, all pose records read on the host",
                    "api": "Encoder.descriptors + Decoder.registration_forward_batch (one C-ABI call each), pinned host "
-                          "input, pose records copied back to pinned memory every step"}
+                          "input (prefetched on a copy stream under the stream's previous step), pose records copied back to pinned memory every "
+                          "step; two steps in flight per stream"}
 
         # ---- batch 1 (BASELINE.json configs[1]/[2]): one frame + one registration at a time, one stream ----
         batch1 = None
